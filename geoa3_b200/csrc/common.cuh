@@ -1,0 +1,52 @@
+// common.cuh — shared device helpers for libgeoa3_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/geoa3_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "geoa3_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+#define GEOA3_CHECK_ARG(cond) \
+  do {                        \
+    if (!(cond)) return GEOA3_EINVAL; \
+  } while (0)
+
+#define GEOA3_LAUNCH_RESULT() ((int)cudaGetLastError())
+
+namespace geoa3 {
+
+constexpr int kNumSMs = 148;  // B200
+
+// Pinned squared distance: t = dx*dx; t = fma(dy,dy,t); t = fma(dz,dz,t)  (never re-associated:
+// explicit round-to-nearest intrinsics are not subject to -fmad contraction).
+__device__ __forceinline__ float dist2(float px, float py, float pz, float qx, float qy, float qz) {
+  float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+  float t = __fmul_rn(dx, dx);
+  t = __fmaf_rn(dy, dy, t);
+  t = __fmaf_rn(dz, dz, t);
+  return t;
+}
+
+// Two pinned squared distances per instruction (Blackwell packed fp32: FADD2/FMUL2/FFMA2 keep the
+// per-lane IEEE rn result, so each half is bit-identical to dist2()).  c* hold two candidates,
+// nq* hold the NEGATED query coordinate in both halves ((c-q)^2 == (q-c)^2 exactly).
+__device__ __forceinline__ float2 dist2x2(float2 cx, float2 cy, float2 cz, float2 nqx, float2 nqy, float2 nqz) {
+  float2 dx = __fadd2_rn(cx, nqx), dy = __fadd2_rn(cy, nqy), dz = __fadd2_rn(cz, nqz);
+  float2 t = __fmul2_rn(dx, dx);
+  t = __ffma2_rn(dy, dy, t);
+  t = __ffma2_rn(dz, dz, t);
+  return t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace geoa3

@@ -1,0 +1,315 @@
+// kappa_loss.cu — curvature (kappa), per-cloud loss reductions and the fused deterministic backward.
+//
+// Both kernels run one CTA per cloud with the cloud resident in shared memory:
+//   forward : kappa_i, borrowed normals, CD / HD(+argmax) / curvature-loss reductions in fixed order;
+//   backward: d(g_cd*CD + g_hd*HD + g_cu*CUR + <g_kappa,kappa>)/d adv.  Scatter terms (Chamfer column
+//             term through istar, curvature neighbour term through nbr) are turned into gathers: a
+//             CSR-by-target list is built in shared memory with a warp-ordered counting sort
+//             (match.any ranks inside a warp, per-warp histograms across warps), so every target sums
+//             its contributions in ascending source order — no float atomics, bitwise reproducible.
+#include "common.cuh"
+#include "csr.cuh"
+
+namespace geoa3 {
+
+constexpr int KL_THREADS = 512;
+constexpr int KL_WARPS = KL_THREADS / 32;
+constexpr float KL_EPS = 1e-12f;  // utility.py:30 _normalize eps
+
+// ---------------------------------------------------------------- block helpers (fixed order)
+__device__ __forceinline__ float block_sum(float v, float* scratch /*KL_WARPS*/) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < KL_WARPS; ++i) t += scratch[i];
+  return t;
+}
+
+// max with lowest index on ties
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* sv, int* si) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { sv[w] = v; si[w] = idx; }
+  __syncthreads();
+  v = sv[0]; idx = si[0];
+#pragma unroll
+  for (int i = 1; i < KL_WARPS; ++i)
+    if (sv[i] > v || (sv[i] == v && si[i] < idx)) { v = sv[i]; idx = si[i]; }
+}
+
+// ---------------------------------------------------------------- forward
+__global__ void __launch_bounds__(KL_THREADS)
+kappa_loss_fwd_kernel(const float* __restrict__ pc, const float* __restrict__ normal, int n_normal,
+                      const int32_t* __restrict__ jstar, const int32_t* __restrict__ nbr, int k,
+                      const float* __restrict__ d_a2o, const float* __restrict__ d_o2a, int m,
+                      const float* __restrict__ kappa_ori, int n, float* __restrict__ kappa,
+                      float* __restrict__ nrm_out, float* __restrict__ cd, float* __restrict__ hd,
+                      int32_t* __restrict__ hd_arg, float* __restrict__ curv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* pts = reinterpret_cast<float4*>(smem_raw);
+  __shared__ float s_f[KL_WARPS];
+  __shared__ int s_i[KL_WARPS];
+
+  const int cloud = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* p = pc + (size_t)cloud * 3 * n;
+  const bool do_kappa = nbr != nullptr && k > 0;
+  if (do_kappa) {
+    for (int i = tid; i < n; i += KL_THREADS) pts[i] = make_float4(p[i], p[n + i], p[2 * n + i], 0.f);
+  }
+  __syncthreads();
+
+  float s1 = 0.f, sc = 0.f, mx = -1.f;
+  int am = 0x7fffffff;
+  const float inv_k = do_kappa ? 1.f / (float)k : 0.f;
+  for (int i = tid; i < n; i += KL_THREADS) {
+    const size_t gi = (size_t)cloud * n + i;
+    const int js = jstar ? jstar[gi] : i;
+    float kap = 0.f;
+    if (do_kappa) {
+      const float* nb = normal + (size_t)cloud * 3 * n_normal;
+      const float nx = nb[js], ny = nb[n_normal + js], nz = nb[2 * n_normal + js];
+      if (nrm_out) {
+        float* no = nrm_out + (size_t)cloud * 3 * n;
+        no[i] = nx; no[n + i] = ny; no[2 * n + i] = nz;
+      }
+      const float4 pi = pts[i];
+      const int32_t* nbi = nbr + gi * k;
+      float acc = 0.f;
+      for (int t = 0; t < k; ++t) {
+        const float4 pj = pts[nbi[t]];
+        const float vx = pj.x - pi.x, vy = pj.y - pi.y, vz = pj.z - pi.z;
+        const float L = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), KL_EPS);
+        const float ux = __fdiv_rn(vx, L), uy = __fdiv_rn(vy, L), uz = __fdiv_rn(vz, L);
+        acc += fabsf(ux * nx + uy * ny + uz * nz);
+      }
+      kap = acc * inv_k;
+      if (kappa) kappa[gi] = kap;
+      if (curv) {
+        const float e = kap - kappa_ori[(size_t)cloud * n_normal + js];
+        sc += e * e;
+      }
+    }
+    if (d_a2o) {
+      const float d = d_a2o[gi];
+      s1 += d;
+      if (d > mx) { mx = d; am = i; }  // ascending i per thread + strict '>' keeps the lowest index
+    }
+  }
+  if (cd || hd || hd_arg) {
+    float s2 = 0.f;
+    if (d_o2a)
+      for (int j = tid; j < m; j += KL_THREADS) s2 += d_o2a[(size_t)cloud * m + j];
+    const float t1 = block_sum(s1, s_f);
+    const float t2 = d_o2a ? block_sum(s2, s_f) : 0.f;
+    block_argmax(mx, am, s_f, s_i);
+    if (tid == 0) {
+      if (cd) cd[cloud] = t1 / (float)n + (d_o2a ? t2 / (float)m : 0.f);
+      if (hd) hd[cloud] = mx;
+      if (hd_arg) hd_arg[cloud] = am;
+    }
+  }
+  if (curv && do_kappa) {
+    const float tc = block_sum(sc, s_f);
+    if (tid == 0) curv[cloud] = tc / (float)n;
+  }
+}
+
+// d|<n, v/|v|>| / dv scaled by f0 = gk/k  (clamp at 1e-12 passes no grad to the norm)
+__device__ __forceinline__ float3 dkappa_dv(float vx, float vy, float vz, float nx, float ny, float nz, float f0) {
+  const float L = sqrtf(vx * vx + vy * vy + vz * vz);
+  float3 r;
+  if (L >= KL_EPS) {
+    const float inv = 1.f / L;
+    const float ux = vx * inv, uy = vy * inv, uz = vz * inv;
+    const float s = ux * nx + uy * ny + uz * nz;
+    const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+    const float f = f0 * sg * inv;
+    r.x = f * (nx - ux * s); r.y = f * (ny - uy * s); r.z = f * (nz - uz * s);
+  } else {
+    const float s = (vx * nx + vy * ny + vz * nz) * 1e12f;
+    const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+    const float f = f0 * sg * 1e12f;
+    r.x = f * nx; r.y = f * ny; r.z = f * nz;
+  }
+  return r;
+}
+
+struct BwdLayout {  // byte offsets into dynamic shared memory
+  int pts, nrm, offs1, offs2, whist, ent1, ent2, total, W;
+};
+
+__global__ void __launch_bounds__(KL_THREADS)
+loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, const float* __restrict__ nrm_adv,
+                const float* __restrict__ kappa_adv, const float* __restrict__ kappa_ori,
+                const int32_t* __restrict__ jstar, const int32_t* __restrict__ istar,
+                const int32_t* __restrict__ nbr, const int32_t* __restrict__ hd_arg,
+                const float* __restrict__ g_cd, const float* __restrict__ g_hd, const float* __restrict__ g_cu,
+                const float* __restrict__ g_kappa, int n, int m, int k, float* __restrict__ grad_adv,
+                BwdLayout lay) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* pts = reinterpret_cast<float4*>(smem_raw + lay.pts);
+  float4* nrm = reinterpret_cast<float4*>(smem_raw + lay.nrm);
+  int* offs1 = reinterpret_cast<int*>(smem_raw + lay.offs1);
+  int* offs2 = reinterpret_cast<int*>(smem_raw + lay.offs2);
+  int* whist = reinterpret_cast<int*>(smem_raw + lay.whist);
+  uint16_t* ent1 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent1);
+  uint16_t* ent2 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent2);
+  __shared__ int scan_scratch[KL_WARPS + 1];
+
+  const int cloud = blockIdx.x, tid = threadIdx.x;
+  const float* a = adv + (size_t)cloud * 3 * n;
+  const float* o = ori + (size_t)cloud * 3 * m;
+  const bool do_curv = k > 0 && nbr != nullptr && (g_cu != nullptr || g_kappa != nullptr);
+  const bool do_col = istar != nullptr && g_cd != nullptr;
+  const float gcd = g_cd ? g_cd[cloud] : 0.f;
+  const float ghd = g_hd ? g_hd[cloud] : 0.f;
+  const float gcu = g_cu ? g_cu[cloud] : 0.f;
+
+  for (int i = tid; i < n; i += KL_THREADS) {
+    const size_t gi = (size_t)cloud * n + i;
+    float gk = 0.f;
+    if (do_curv) {
+      if (g_cu) gk = gcu * (2.f / (float)n) * (kappa_adv[gi] - kappa_ori[(size_t)cloud * m + jstar[gi]]);
+      if (g_kappa) gk += g_kappa[gi];
+      const float* nn = nrm_adv + (size_t)cloud * 3 * n;
+      nrm[i] = make_float4(nn[i], nn[n + i], nn[2 * n + i], 0.f);
+    }
+    pts[i] = make_float4(a[i], a[n + i], a[2 * n + i], gk);
+  }
+  __syncthreads();
+  if (do_curv) build_csr<KL_THREADS>(nbr + (size_t)cloud * n * k, n * k, n, k, offs1, whist, lay.W, ent1, scan_scratch);
+  if (do_col) build_csr<KL_THREADS>(istar + (size_t)cloud * m, m, n, 1, offs2, whist, lay.W, ent2, scan_scratch);
+
+  const int ha = (g_hd && hd_arg) ? hd_arg[cloud] : -1;
+  const float w_row = gcd * (2.f / (float)n), w_col = gcd * (2.f / (float)m);
+  const float inv_k = k > 0 ? 1.f / (float)k : 0.f;
+  for (int p = tid; p < n; p += KL_THREADS) {
+    const size_t gp = (size_t)cloud * n + p;
+    const float4 ap = pts[p];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (g_cd || ha == p) {
+      const int js = jstar[gp];
+      const float rx = ap.x - o[js], ry = ap.y - o[m + js], rz = ap.z - o[2 * m + js];
+      if (g_cd) { gx = w_row * rx; gy = w_row * ry; gz = w_row * rz; }
+      if (do_col) {
+        const int e1 = offs2[p + 1];
+        for (int e = offs2[p]; e < e1; ++e) {
+          const int j = ent2[e];
+          gx += w_col * (ap.x - o[j]); gy += w_col * (ap.y - o[m + j]); gz += w_col * (ap.z - o[2 * m + j]);
+        }
+      }
+      if (ha == p) { gx += ghd * 2.f * rx; gy += ghd * 2.f * ry; gz += ghd * 2.f * rz; }
+    }
+    if (do_curv) {
+      // own term: -sum_m d kappa_p / d v_pm
+      const float4 np_ = nrm[p];
+      const float f0 = ap.w * inv_k;
+      const int32_t* nbp = nbr + gp * k;
+      float ox = 0.f, oy = 0.f, oz = 0.f;
+      for (int t = 0; t < k; ++t) {
+        const float4 aj = pts[nbp[t]];
+        const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
+        ox += dv.x; oy += dv.y; oz += dv.z;
+      }
+      gx -= ox; gy -= oy; gz -= oz;
+      // incoming terms: every i that lists p as a neighbour, ascending i
+      const int e1 = offs1[p + 1];
+      for (int e = offs1[p]; e < e1; ++e) {
+        const int i = ent1[e];
+        const float4 ai = pts[i];
+        const float4 ni = nrm[i];
+        const float3 dv = dkappa_dv(ap.x - ai.x, ap.y - ai.y, ap.z - ai.z, ni.x, ni.y, ni.z, ai.w * inv_k);
+        gx += dv.x; gy += dv.y; gz += dv.z;
+      }
+    }
+    float* g = grad_adv + (size_t)cloud * 3 * n;
+    g[p] = gx; g[n + p] = gy; g[2 * n + p] = gz;
+  }
+}
+
+static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdLayout* L) {
+  const int budget = 227 * 1024 - 256;
+  for (int W = KL_WARPS; W >= 1; W >>= 1) {
+    int off = 0;
+    auto take = [&](size_t bytes) { int o = off; off += (int)((bytes + 15) & ~(size_t)15); return o; };
+    L->pts = take((size_t)16 * n);
+    L->nrm = take(do_curv ? (size_t)16 * n : 0);
+    L->offs1 = take(do_curv ? (size_t)4 * (n + 1) : 0);
+    L->offs2 = take(do_col ? (size_t)4 * (n + 1) : 0);
+    L->whist = take((do_curv || do_col) ? (size_t)4 * W * n : 0);
+    L->ent1 = take(do_curv ? (size_t)2 * n * k : 0);
+    L->ent2 = take(do_col ? (size_t)2 * m : 0);
+    L->total = off;
+    L->W = W;
+    // prefer two resident CTAs per SM while at least 4 builder warps remain
+    if (off <= budget / 2 || (W <= 4 && off <= budget)) return true;
+  }
+  return L->total <= budget;
+}
+
+}  // namespace geoa3
+
+extern "C" int geoa3_kappa_loss_fwd(const float* pc, const float* normal, const int32_t* jstar,
+                                    const int32_t* nbr, int k, const float* d_a2o, const float* d_o2a,
+                                    const float* kappa_ori, int b, int n, int m, float* kappa, float* nrm_out,
+                                    float* cd, float* hd, int32_t* hd_arg, float* curv, geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(pc && b > 0 && n > 0 && m > 0);
+  const bool do_kappa = nbr != nullptr && k > 0;
+  if (do_kappa) GEOA3_CHECK_ARG(normal);
+  if (!jstar && do_kappa) GEOA3_CHECK_ARG(m == n);
+  if (curv) GEOA3_CHECK_ARG(do_kappa && kappa_ori && jstar);
+  if (cd || hd || hd_arg) GEOA3_CHECK_ARG(d_a2o);
+  const size_t smem = do_kappa ? (size_t)16 * n : 0;
+  if (smem > 227 * 1024 - 1024) return GEOA3_EUNSUPPORTED;
+  static bool attr_done = false;  // idempotent attribute: a benign race at worst repeats the call
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kappa_loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024 - 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  kappa_loss_fwd_kernel<<<b, KL_THREADS, smem, (cudaStream_t)stream>>>(
+      pc, normal, m, jstar, nbr, k, d_a2o, d_o2a, m, kappa_ori, n, kappa, nrm_out, cd, hd, hd_arg, curv);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* nrm_adv, const float* kappa_adv,
+                              const float* kappa_ori, const int32_t* jstar, const int32_t* istar,
+                              const int32_t* nbr, const int32_t* hd_arg, const float* g_cd, const float* g_hd,
+                              const float* g_cu, const float* g_kappa, int b, int n, int m, int k,
+                              float* grad_adv, geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(adv && grad_adv && b > 0 && n > 0 && m > 0 && k >= 0);
+  if (g_cd || g_hd) GEOA3_CHECK_ARG(ori && jstar);
+  if (g_hd) GEOA3_CHECK_ARG(hd_arg);
+  const bool do_curv = k > 0 && nbr && (g_cu || g_kappa);
+  if (do_curv) GEOA3_CHECK_ARG(nrm_adv);
+  if (g_cu && do_curv) GEOA3_CHECK_ARG(kappa_adv && kappa_ori && jstar);
+  const bool do_col = istar && g_cd;
+  if (n > 65535 || m > 65535) return GEOA3_EUNSUPPORTED;  // CSR entries are uint16
+  BwdLayout L;
+  if (!plan_bwd_layout(n, m, k, do_curv, do_col, &L)) return GEOA3_EUNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024 - 256);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  loss_bwd_kernel<<<b, KL_THREADS, L.total, (cudaStream_t)stream>>>(adv, ori, nrm_adv, kappa_adv, kappa_ori, jstar,
+                                                                    istar, nbr, hd_arg, g_cd, g_hd, g_cu, g_kappa, n,
+                                                                    m, k, grad_adv, L);
+  return GEOA3_LAUNCH_RESULT();
+}

@@ -1,0 +1,149 @@
+// knn.cu — exact K-nearest-neighbour selection (K = k+1 <= 33) for the curvature losses.
+//
+// Thread-per-query brute force, candidates streamed through shared memory as SoA float4 broadcasts
+// and evaluated two at a time on the packed fp32 pipe (pinned fma-chain arithmetic, see common.cuh).
+// Each thread keeps its K best (dist, idx) pairs sorted in registers; tau = current K-th distance.
+// A candidate passes only if d < tau (strict; candidates are visited in ascending index, so among
+// equal distances the lowest indices survive => lexicographic (dist, idx) order, the pinned rule).
+// Passing candidates are NOT inserted on the spot (that would serialise the warp on its slowest
+// lane every step): they are appended to a small per-thread queue in shared memory and the warp
+// drains all queues together — a branch-free sorted-insert network executed by all 32 lanes — when
+// any lane's queue is nearly full.  The queue preserves arrival order, so ties keep their order.
+#include "common.cuh"
+
+namespace geoa3 {
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_CHUNK = 2048;  // candidates per shared-memory pass
+constexpr int KNN_QDEPTH = 8;    // queue slots per thread
+
+template <int K>
+struct TopK {
+  float d[K];
+  int i[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int l = 0; l < K; ++l) { d[l] = __int_as_float(0x7f800000); i[l] = -1; }
+  }
+  // sorted insert of (x, xi); elements equal to x stay in front of it (arrival order = index order)
+  __device__ __forceinline__ void insert(float x, int xi) {
+    float cd = x;
+    int ci = xi;
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      const bool p = x < d[l];
+      const float od = d[l];
+      const int oi = i[l];
+      d[l] = p ? cd : od;
+      i[l] = p ? ci : oi;
+      cd = p ? od : cd;
+      ci = p ? oi : ci;
+    }
+  }
+  __device__ __forceinline__ float tau() const { return d[K - 1]; }
+};
+
+template <int K>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n, int m, int kout, int drop,
+           int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  __shared__ __align__(16) float sx[KNN_CHUNK];
+  __shared__ __align__(16) float sy[KNN_CHUNK];
+  __shared__ __align__(16) float sz[KNN_CHUNK];
+  __shared__ float qd[KNN_QDEPTH][KNN_THREADS];
+  __shared__ int qj[KNN_QDEPTH][KNN_THREADS];
+
+  const int cloud = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x * KNN_THREADS + tid;
+  const float* qbase = query + (size_t)cloud * 3 * n;
+  const float* cbase = ref + (size_t)cloud * 3 * m;
+  const int qq = min(qi, n - 1);
+  const float qx = qbase[qq], qy = qbase[n + qq], qz = qbase[2 * n + qq];
+  const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+
+  TopK<K> top;
+  top.init();
+  float tau = top.tau();
+  int cnt = 0;
+
+  auto drain = [&]() {
+    const int mx = __reduce_max_sync(0xffffffffu, cnt);
+    for (int r = 0; r < mx; ++r) {
+      // lanes without an r-th entry feed +inf, which the network leaves in the carry
+      const float x = r < cnt ? qd[r][tid] : __int_as_float(0x7f800000);
+      const int xi = r < cnt ? qj[r][tid] : -1;
+      top.insert(x, xi);
+    }
+    cnt = 0;
+    tau = top.tau();
+  };
+
+  for (int c0 = 0; c0 < m; c0 += KNN_CHUNK) {
+    const int cn = min(KNN_CHUNK, m - c0);
+    const int cn4 = (cn + 3) & ~3;
+    __syncthreads();
+    for (int t = tid; t < cn4; t += KNN_THREADS) {
+      const bool ok = t < cn;
+      sx[t] = ok ? cbase[c0 + t] : __int_as_float(0x7f800000);  // +inf padding never passes d < tau
+      sy[t] = ok ? cbase[m + c0 + t] : 0.f;
+      sz[t] = ok ? cbase[2 * m + c0 + t] : 0.f;
+    }
+    __syncthreads();
+    for (int j = 0; j < cn4; j += 4) {
+      const float4 cx = *reinterpret_cast<const float4*>(sx + j);
+      const float4 cy = *reinterpret_cast<const float4*>(sy + j);
+      const float4 cz = *reinterpret_cast<const float4*>(sz + j);
+      const float2 d01 = dist2x2(make_float2(cx.x, cx.y), make_float2(cy.x, cy.y), make_float2(cz.x, cz.y), nqx, nqy, nqz);
+      const float2 d23 = dist2x2(make_float2(cx.z, cx.w), make_float2(cy.z, cy.w), make_float2(cz.z, cz.w), nqx, nqy, nqz);
+      const int jj = c0 + j;
+      if (d01.x < tau) { qd[cnt][tid] = d01.x; qj[cnt][tid] = jj; ++cnt; }
+      if (d01.y < tau) { qd[cnt][tid] = d01.y; qj[cnt][tid] = jj + 1; ++cnt; }
+      if (d23.x < tau) { qd[cnt][tid] = d23.x; qj[cnt][tid] = jj + 2; ++cnt; }
+      if (d23.y < tau) { qd[cnt][tid] = d23.y; qj[cnt][tid] = jj + 3; ++cnt; }
+      if (__any_sync(0xffffffffu, cnt > KNN_QDEPTH - 4)) drain();
+    }
+  }
+  drain();
+
+  if (qi < n) {
+    int32_t* io = idx_out + ((size_t)cloud * n + qi) * kout;
+    float* dn = dist_out ? dist_out + ((size_t)cloud * n + qi) * kout : nullptr;
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      const int o = l - drop;
+      if (o >= 0 && o < kout) {
+        io[o] = top.i[l];
+        if (dn) dn[o] = top.d[l];
+      }
+    }
+  }
+}
+
+template <int K>
+static int launch_knn(const float* query, const float* ref, int b, int n, int m, int kout, int drop,
+                      int32_t* idx, float* dist, cudaStream_t s) {
+  dim3 grid(ceil_div(n, KNN_THREADS), b, 1);
+  knn_kernel<K><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, idx, dist);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+}  // namespace geoa3
+
+extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int m, int K, int drop,
+                         int32_t* idx, float* dist, geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(query && ref && idx);
+  GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K);
+  if (K > GEOA3_KNN_MAX_K || b > 65535) return GEOA3_EUNSUPPORTED;
+  if (K > m) return GEOA3_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int kout = K - drop;
+  // the list size is a compile-time constant (register arrays); a larger list than requested is still
+  // exact: the first K entries of the top-K' (K' >= K) are the top-K.
+  if (K <= 3) return launch_knn<3>(query, ref, b, n, m, kout, drop, idx, dist, s);
+  if (K <= 5) return launch_knn<5>(query, ref, b, n, m, kout, drop, idx, dist, s);
+  if (K <= 9) return launch_knn<9>(query, ref, b, n, m, kout, drop, idx, dist, s);
+  if (K <= 17) return launch_knn<17>(query, ref, b, n, m, kout, drop, idx, dist, s);
+  return launch_knn<33>(query, ref, b, n, m, kout, drop, idx, dist, s);
+}

@@ -1,0 +1,491 @@
+// pointnet2.cu — sampling / grouping ops of PointNet++ (FPS, ball query, group, gather + gradients,
+// three_nn / three_interpolate) for sm_100a.
+//
+//  * FPS keeps the whole cloud state on chip: coordinates and the running min-distance of every point
+//    live in registers (P points per thread), the cloud is mirrored in shared memory only to broadcast
+//    the last selected point.  One round = P fused distance updates + a 2-instruction warp arg-max
+//    (REDUX on the packed key) + ONE block barrier (double-buffered partials), instead of the
+//    reference's 10 barriers and global-memory temp round trip.  The selection order of the reference
+//    (max distance, ties -> smallest (k mod BS, k), points with |p|^2 <= 1e-3 never touched) is encoded
+//    in a 64-bit sort key so any thread layout reproduces it bit for bit.
+//  * ball query runs a warp per centroid: 64 candidates per step on the packed fp32 pipe, ballots give
+//    the in-order write positions, the scan stops as soon as nsample hits are found.
+//  * group_points stages the gathered rows in shared memory (random 4-byte global gathers would cost a
+//    wavefront per sector) and writes float4 along nsample — the op is output-write bound.
+//  * scatter gradients (group / gather / three_interpolate) gather through a deterministic CSR (csr.cuh).
+#include "common.cuh"
+#include "csr.cuh"
+
+namespace geoa3 {
+
+// ============================================================================ FPS
+constexpr int FPS_MAX_WARPS = 32;
+
+// reference block size: opt_n_threads(n) = clamp(2^floor(log2 n), 1, 512) (cuda_utils.h:13-19)
+static int ref_fps_block(int n) {
+  int p = 1;
+  while (p * 2 <= n && p < 512) p *= 2;
+  return p;
+}
+
+template <int P>
+__global__ void __launch_bounds__(1024)
+fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int32_t* __restrict__ idxs) {
+  extern __shared__ __align__(16) float s_xyz[];  // [3][n] SoA mirror of the cloud
+  __shared__ unsigned long long s_part[2][FPS_MAX_WARPS];
+
+  const int cloud = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, w = tid >> 5, nw = T >> 5;
+  const float* p = xyz + (size_t)cloud * n * 3;
+  int32_t* out = idxs + (size_t)cloud * m;
+
+  float px[P], py[P], pz[P], temp[P];
+  unsigned tk[P];  // low word of the sort key; 0 => point is frozen (skipped) or out of range
+#pragma unroll
+  for (int t = 0; t < P; ++t) {
+    const int k = tid + t * T;
+    px[t] = py[t] = pz[t] = 0.f;
+    temp[t] = 1e10f;
+    tk[t] = 0u;
+    if (k < n) {
+      px[t] = p[k * 3]; py[t] = p[k * 3 + 1]; pz[t] = p[k * 3 + 2];
+      s_xyz[k] = px[t]; s_xyz[n + k] = py[t]; s_xyz[2 * n + k] = pz[t];
+      const float mag = __fmaf_rn(pz[t], pz[t], __fmaf_rn(py[t], py[t], __fmul_rn(px[t], px[t])));
+      if (!((double)mag <= 1e-3)) tk[t] = ~(((unsigned)(k % ref_bs) << 20) | (unsigned)k);
+    }
+  }
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = s_xyz[old], y1 = s_xyz[n + old], z1 = s_xyz[2 * n + old];
+    unsigned bh = 0u, bl = 0u;  // best (hi, lo); (0,0) = no candidate
+#pragma unroll
+    for (int t = 0; t < P; ++t) {
+      if (tk[t] != 0u) {
+        const float d = dist2(px[t], py[t], pz[t], x1, y1, z1);
+        temp[t] = fminf(d, temp[t]);
+        const unsigned h = __float_as_uint(temp[t]);
+        if (h > bh || (h == bh && tk[t] > bl)) { bh = h; bl = tk[t]; }
+      }
+    }
+    // warp arg-max of the 64-bit key in two REDUX steps
+    const unsigned mh = __reduce_max_sync(0xffffffffu, bh);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
+    if (lane == 0) s_part[j & 1][w] = ((unsigned long long)mh << 32) | ml;
+    __syncthreads();
+    unsigned long long best = 0ull;
+    for (int i = 0; i < nw; ++i) {
+      const unsigned long long v = s_part[j & 1][i];
+      best = v > best ? v : best;
+    }
+    const unsigned lo = (unsigned)best;
+    old = lo != 0u ? (int)((~lo) & 0xFFFFFu) : 0;
+    if (tid == 0) out[j] = old;
+  }
+}
+
+// ============================================================================ ball query
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_PER_WARP = 8;  // centroids handled sequentially by one warp
+constexpr int BQ_MAX_NS = 256;
+
+__global__ void __launch_bounds__(BQ_WARPS * 32)
+ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int n, int m, float radius,
+                  int nsample, int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) float s_pts[];  // [3][n64] SoA, padded to a multiple of 64 with +inf
+  __shared__ int s_row[BQ_WARPS][BQ_MAX_NS];
+  const int cloud = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n64 = (n + 63) & ~63;
+  const float* p = xyz + (size_t)cloud * n * 3;
+  float* sx = s_pts; float* sy = s_pts + n64; float* sz = s_pts + 2 * n64;
+  for (int i = tid; i < n64; i += BQ_WARPS * 32) {
+    const bool ok = i < n;
+    sx[i] = ok ? p[i * 3] : __int_as_float(0x7f800000);  // padding is never inside a ball
+    sy[i] = ok ? p[i * 3 + 1] : 0.f;
+    sz[i] = ok ? p[i * 3 + 2] : 0.f;
+  }
+  __syncthreads();
+  const float r2 = __fmul_rn(radius, radius);
+  const unsigned lt = (1u << lane) - 1u;
+  int* row = s_row[w];
+  const int c_beg = (blockIdx.x * BQ_WARPS + w) * BQ_PER_WARP;
+  for (int c = c_beg; c < min(m, c_beg + BQ_PER_WARP); ++c) {
+    const float* q = new_xyz + ((size_t)cloud * m + c) * 3;
+    const float qx = -q[0], qy = -q[1], qz = -q[2];
+    const float2 nqx = make_float2(qx, qx), nqy = make_float2(qy, qy), nqz = make_float2(qz, qz);
+    int cnt = 0;
+    for (int j0 = 0; j0 < n64 && cnt < nsample; j0 += 64) {
+      const int ja = j0 + lane, jb = j0 + 32 + lane;
+      const float2 d = dist2x2(make_float2(sx[ja], sx[jb]), make_float2(sy[ja], sy[jb]), make_float2(sz[ja], sz[jb]),
+                               nqx, nqy, nqz);
+      const bool ha = d.x < r2, hb = d.y < r2;
+      const unsigned ba = __ballot_sync(0xffffffffu, ha), bb = __ballot_sync(0xffffffffu, hb);
+      const int pa = cnt + __popc(ba & lt);
+      if (ha && pa < nsample) row[pa] = ja;
+      cnt += __popc(ba);
+      const int pb = cnt + __popc(bb & lt);
+      if (hb && pb < nsample) row[pb] = jb;
+      cnt += __popc(bb);
+    }
+    __syncwarp();
+    cnt = min(cnt, nsample);
+    const int first = cnt > 0 ? row[0] : 0;  // first-hit fill; a centroid with no hit keeps zeros
+    int32_t* o = idx + ((size_t)cloud * m + c) * nsample;
+    for (int l = lane; l < nsample; l += 32) o[l] = l < cnt ? row[l] : first;
+    __syncwarp();
+  }
+}
+
+// ============================================================================ group_points (forward)
+constexpr int GP_THREADS = 256;
+constexpr int GP_CC = 16;        // channels staged per CTA
+constexpr int GP_ETILE = 8192;   // (j,k) positions per CTA
+
+__global__ void __launch_bounds__(GP_THREADS)
+group_points_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx, int c, int n, int E,
+                    float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_rows[];  // [cc][n]
+  const int cloud = blockIdx.z, c0 = blockIdx.y * GP_CC, cc = min(GP_CC, c - c0);
+  const int tid = threadIdx.x;
+  const float* src = points + ((size_t)cloud * c + c0) * n;
+  for (int i = tid; i < cc * n; i += GP_THREADS) s_rows[i] = src[i];
+  __syncthreads();
+  const int32_t* ix = idx + (size_t)cloud * E;
+  float* dst = out + ((size_t)cloud * c + c0) * E;
+  const int e_beg = blockIdx.x * GP_ETILE, e_end = min(E, e_beg + GP_ETILE);
+  if ((E & 3) == 0) {
+    for (int e = e_beg + tid * 4; e < e_end; e += GP_THREADS * 4) {
+      const int4 i4 = *reinterpret_cast<const int4*>(ix + e);
+      for (int l = 0; l < cc; ++l) {
+        const float* r = s_rows + l * n;
+        const float4 v = make_float4(r[i4.x], r[i4.y], r[i4.z], r[i4.w]);
+        __stcs(reinterpret_cast<float4*>(dst + (size_t)l * E + e), v);  // streaming: output is write-once
+      }
+    }
+  } else {
+    for (int e = e_beg + tid; e < e_end; e += GP_THREADS) {
+      const int i1 = ix[e];
+      for (int l = 0; l < cc; ++l) dst[(size_t)l * E + e] = s_rows[l * n + i1];
+    }
+  }
+}
+
+// ============================================================================ CSR in global workspace
+// workspace layout per cloud: offs[n+1] ints, then ent[E] ints
+constexpr int CSRG_THREADS = 512;
+
+__global__ void __launch_bounds__(CSRG_THREADS)
+csr_global_kernel(const int32_t* __restrict__ idx, int E, int n, int W, int* __restrict__ ws) {
+  extern __shared__ __align__(16) int s_whist[];
+  __shared__ int scan_scratch[CSRG_THREADS / 32 + 1];
+  const int cloud = blockIdx.x;
+  int* offs = ws + (size_t)cloud * (n + 1 + E);
+  int* ent = offs + n + 1;
+  build_csr<CSRG_THREADS>(idx + (size_t)cloud * E, E, n, 1, offs, s_whist, W, ent, scan_scratch);
+}
+
+// grad_points[b][c][p] = sum over segment(p) of grad_out[b][c][e] (ascending e), optional weights
+constexpr int GG_THREADS = 256;
+
+__global__ void __launch_bounds__(GG_THREADS)
+csr_gather_grad_kernel(const float* __restrict__ grad_out, const float* __restrict__ weight, const int* __restrict__ ws,
+                       int c, int n, int E, int e_div, int tile, float* __restrict__ grad_points) {
+  // grad_out rows have E/e_div entries per channel (e_div = 3 for three_interpolate, where the three
+  // (idx,weight) slots of one output share one grad_out value); weight (nullable) is [b][E].
+  extern __shared__ __align__(16) float s_go[];  // one tile of the row
+  const int cloud = blockIdx.y, ch = blockIdx.x, tid = threadIdx.x;
+  const int Eg = E / e_div;
+  const int* offs = ws + (size_t)cloud * (n + 1 + E);
+  const int* ent = offs + n + 1;
+  const float* go = grad_out + ((size_t)cloud * c + ch) * Eg;
+  const float* wt = weight ? weight + (size_t)cloud * E : nullptr;
+  float* gp = grad_points + ((size_t)cloud * c + ch) * n;
+  if (tile >= Eg) {  // whole row fits
+    for (int i = tid; i < Eg; i += GG_THREADS) s_go[i] = go[i];
+    __syncthreads();
+    for (int p = tid; p < n; p += GG_THREADS) {
+      float acc = 0.f;
+      const int e1 = offs[p + 1];
+      for (int t = offs[p]; t < e1; ++t) {
+        const int e = ent[t];
+        acc += wt ? s_go[e / e_div] * wt[e] : s_go[e];
+      }
+      gp[p] = acc;
+    }
+  } else {  // tiled over the source range; segments are ascending so each thread keeps a cursor
+    constexpr int MAXP = 8;
+    float acc[MAXP];
+    int cur[MAXP];
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) {
+      const int p = tid + q * GG_THREADS;
+      acc[q] = 0.f;
+      cur[q] = p < n ? offs[p] : 0;
+    }
+    for (int t0 = 0; t0 < Eg; t0 += tile) {
+      const int tn = min(tile, Eg - t0);
+      __syncthreads();
+      for (int i = tid; i < tn; i += GG_THREADS) s_go[i] = go[t0 + i];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < MAXP; ++q) {
+        const int p = tid + q * GG_THREADS;
+        if (p < n) {
+          const int e1 = offs[p + 1];
+          int t = cur[q];
+          while (t < e1) {
+            const int e = ent[t];
+            const int g = e / e_div;
+            if (g >= t0 + tn) break;
+            acc[q] += wt ? s_go[g - t0] * wt[e] : s_go[g - t0];
+            ++t;
+          }
+          cur[q] = t;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) {
+      const int p = tid + q * GG_THREADS;
+      if (p < n) gp[p] = acc[q];
+    }
+  }
+}
+
+// ============================================================================ gather_points (+grad)
+__global__ void gather_points_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx, int c, int n,
+                                     int m, float* __restrict__ out) {
+  const int cloud = blockIdx.z, ch = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) out[((size_t)cloud * c + ch) * m + j] = points[((size_t)cloud * c + ch) * n + idx[(size_t)cloud * m + j]];
+}
+
+// ============================================================================ three_nn / three_interpolate
+constexpr int TN_THREADS = 128;
+constexpr int TN_CHUNK = 2048;
+
+__global__ void __launch_bounds__(TN_THREADS)
+three_nn_kernel(const float* __restrict__ unknown, const float* __restrict__ known, int n, int m,
+                float* __restrict__ dist2o, int32_t* __restrict__ idxo) {
+  __shared__ float sx[TN_CHUNK], sy[TN_CHUNK], sz[TN_CHUNK];
+  const int cloud = blockIdx.y, tid = threadIdx.x;
+  const int j = blockIdx.x * TN_THREADS + tid;
+  const float* u = unknown + ((size_t)cloud * n + min(j, n - 1)) * 3;
+  const float ux = u[0], uy = u[1], uz = u[2];
+  const float* kn = known + (size_t)cloud * m * 3;
+  // reference keeps best1..3 as doubles initialised to 1e40 (interpolate_gpu.cu:27): a float candidate
+  // always compares below that, so +inf sentinels with a strict '<' reproduce it, except that a row with
+  // fewer than 3 known points keeps index 0 and the (float)1e40 = +inf distance — same here.
+  float b1 = __int_as_float(0x7f800000), b2 = b1, b3 = b1;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int c0 = 0; c0 < m; c0 += TN_CHUNK) {
+    const int cn = min(TN_CHUNK, m - c0);
+    __syncthreads();
+    for (int t = tid; t < cn; t += TN_THREADS) {
+      sx[t] = kn[(c0 + t) * 3]; sy[t] = kn[(c0 + t) * 3 + 1]; sz[t] = kn[(c0 + t) * 3 + 2];
+    }
+    __syncthreads();
+    for (int t = 0; t < cn; ++t) {
+      const float d = dist2(ux, uy, uz, sx[t], sy[t], sz[t]);
+      const int k = c0 + t;
+      if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+      else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+      else if (d < b3) { b3 = d; i3 = k; }
+    }
+  }
+  if (j < n) {
+    float* dn = dist2o + ((size_t)cloud * n + j) * 3;
+    int32_t* io = idxo + ((size_t)cloud * n + j) * 3;
+    dn[0] = b1; dn[1] = b2; dn[2] = b3;
+    io[0] = i1; io[1] = i2; io[2] = i3;
+  }
+}
+
+__global__ void three_interpolate_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx,
+                                         const float* __restrict__ weight, int c, int m, int n,
+                                         float* __restrict__ out) {
+  const int cloud = blockIdx.z, ch = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const size_t o = ((size_t)cloud * n + j) * 3;
+  const float* p = points + ((size_t)cloud * c + ch) * m;
+  // same expression shape as interpolate_gpu.cu:98-99 (mul, fma, fma under default contraction)
+  out[((size_t)cloud * c + ch) * n + j] =
+      __fmaf_rn(p[idx[o + 2]], weight[o + 2], __fmaf_rn(p[idx[o + 1]], weight[o + 1], __fmul_rn(p[idx[o]], weight[o])));
+}
+
+static size_t csr_ws_bytes(int b, int n, int E) { return (size_t)b * ((size_t)n + 1 + (size_t)E) * sizeof(int); }
+
+static int pick_W(int n, int threads) {
+  int W = threads / 32;
+  while (W > 1 && (size_t)W * n * 4 > 96 * 1024) W >>= 1;
+  return W;
+}
+
+static int run_csr_grad(const float* grad_out, const float* weight, const int32_t* idx, int b, int c, int n, int E,
+                        int e_div, float* grad_points, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (workspace_bytes < csr_ws_bytes(b, n, E) || !workspace) return GEOA3_EWORKSPACE;
+  const int W = pick_W(n, CSRG_THREADS);
+  const size_t sm1 = (size_t)W * n * 4;
+  if (sm1 > 200 * 1024) return GEOA3_EUNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(csr_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(csr_gather_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  csr_global_kernel<<<b, CSRG_THREADS, sm1, s>>>(idx, E, n, W, (int*)workspace);
+  int err = GEOA3_LAUNCH_RESULT();
+  if (err) return err;
+  const int Eg = E / e_div;
+  int tile = Eg;
+  if ((size_t)Eg * 4 > 96 * 1024) {
+    tile = 24 * 1024;  // 96 KB tiles, two CTAs per SM
+    if (n > 8 * GG_THREADS) return GEOA3_EUNSUPPORTED;
+  }
+  csr_gather_grad_kernel<<<dim3(c, b), GG_THREADS, (size_t)tile * 4, s>>>(grad_out, weight, (const int*)workspace, c, n, E,
+                                                                         e_div, tile, grad_points);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+}  // namespace geoa3
+
+using namespace geoa3;
+
+extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int m, int32_t* idx,
+                                             geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(xyz && idx && b > 0 && n > 0 && m > 0);
+  if (n >= (1 << 20) || (size_t)n * 12 > 200 * 1024) return GEOA3_EUNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = (size_t)n * 12;
+  const int bs = ref_fps_block(n);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(fps_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  if (n <= 4096) {
+    const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
+    fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, idx);
+  } else if (n <= 8192) {
+    fps_kernel<8><<<b, 1024, smem, s>>>(xyz, n, m, bs, idx);
+  } else if (n <= 16384) {
+    fps_kernel<16><<<b, 1024, smem, s>>>(xyz, n, m, bs, idx);
+  } else {
+    return GEOA3_EUNSUPPORTED;
+  }
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius,
+                                int nsample, int32_t* idx, geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(new_xyz && xyz && idx && b > 0 && n > 0 && m > 0 && nsample > 0);
+  if (nsample > BQ_MAX_NS || b > 65535) return GEOA3_EUNSUPPORTED;
+  const size_t smem = (size_t)((n + 63) & ~63) * 12;
+  if (smem > 200 * 1024) return GEOA3_EUNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(m, BQ_WARPS * BQ_PER_WARP), b);
+  ball_query_kernel<<<grid, BQ_WARPS * 32, smem, (cudaStream_t)stream>>>(new_xyz, xyz, n, m, radius, nsample, idx);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_group_points(const float* points, const int32_t* idx, int b, int c, int n, int npoints,
+                                  int nsample, float* out, geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(points && idx && out && b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0);
+  if (b > 65535 || (size_t)n * 4 * 1 > 200 * 1024) return GEOA3_EUNSUPPORTED;
+  const int E = npoints * nsample;
+  // channels per CTA limited by shared memory (GP_CC rows of n floats)
+  const size_t smem = (size_t)(c < GP_CC ? c : GP_CC) * n * 4;
+  if (smem > 200 * 1024) return GEOA3_EUNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(group_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(E, GP_ETILE), ceil_div(c, GP_CC), b);
+  group_points_kernel<<<grid, GP_THREADS, smem, (cudaStream_t)stream>>>(points, idx, c, n, E, out);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" size_t geoa3_group_points_grad_workspace_bytes(int b, int n, int npoints, int nsample) {
+  return csr_ws_bytes(b, n, npoints * nsample);
+}
+
+extern "C" int geoa3_group_points_grad(const float* grad_out, const int32_t* idx, int b, int c, int n, int npoints,
+                                       int nsample, float* grad_points, void* workspace, size_t workspace_bytes,
+                                       geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(grad_out && idx && grad_points && b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0);
+  if (b > 65535 || c > 65535) return GEOA3_EUNSUPPORTED;
+  return run_csr_grad(grad_out, nullptr, idx, b, c, n, npoints * nsample, 1, grad_points, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int geoa3_gather_points(const float* points, const int32_t* idx, int b, int c, int n, int m, float* out,
+                                   geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(points && idx && out && b > 0 && c > 0 && n > 0 && m > 0);
+  if (b > 65535 || c > 65535) return GEOA3_EUNSUPPORTED;
+  gather_points_kernel<<<dim3(ceil_div(m, 256), c, b), 256, 0, (cudaStream_t)stream>>>(points, idx, c, n, m, out);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_gather_points_grad(const float* grad_out, const int32_t* idx, int b, int c, int n, int m,
+                                        float* grad_points, void* workspace, size_t workspace_bytes,
+                                        geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(grad_out && idx && grad_points && b > 0 && c > 0 && n > 0 && m > 0);
+  if (b > 65535 || c > 65535) return GEOA3_EUNSUPPORTED;
+  return run_csr_grad(grad_out, nullptr, idx, b, c, n, m, 1, grad_points, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int geoa3_three_nn(const float* unknown, const float* known, int b, int n, int m, float* dist2, int32_t* idx,
+                              geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(unknown && known && dist2 && idx && b > 0 && n > 0 && m > 0);
+  if (b > 65535) return GEOA3_EUNSUPPORTED;
+  three_nn_kernel<<<dim3(ceil_div(n, TN_THREADS), b), TN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist2,
+                                                                                            idx);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_three_interpolate(const float* points, const int32_t* idx, const float* weight, int b, int c,
+                                       int m, int n, float* out, geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(points && idx && weight && out && b > 0 && c > 0 && m > 0 && n > 0);
+  if (b > 65535 || c > 65535) return GEOA3_EUNSUPPORTED;
+  three_interpolate_kernel<<<dim3(ceil_div(n, 256), c, b), 256, 0, (cudaStream_t)stream>>>(points, idx, weight, c, m, n,
+                                                                                          out);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_three_interpolate_grad(const float* grad_out, const int32_t* idx, const float* weight, int b,
+                                            int c, int n, int m, float* grad_points, void* workspace,
+                                            size_t workspace_bytes, geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(grad_out && idx && weight && grad_points && b > 0 && c > 0 && n > 0 && m > 0);
+  if (b > 65535 || c > 65535) return GEOA3_EUNSUPPORTED;
+  // targets are the m known points, sources the 3n (point, slot) pairs
+  return run_csr_grad(grad_out, weight, idx, b, c, m, 3 * n, 3, grad_points, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int geoa3_version(void) { return 1000; }
+
+extern "C" const char* geoa3_error_string(int code) {
+  switch (code) {
+    case GEOA3_OK: return "ok";
+    case GEOA3_EINVAL: return "geoa3: invalid argument (null pointer or non-positive size)";
+    case GEOA3_EUNSUPPORTED: return "geoa3: size outside the supported range of the sm_100a kernels";
+    case GEOA3_EWORKSPACE: return "geoa3: workspace missing or too small";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "geoa3: unknown error";
+  }
+}

@@ -1,0 +1,183 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point of
+include/geoa3_b200.h).  They allocate outputs with torch, launch on torch's current stream and raise
+RuntimeError on any non-zero return code.  No autograd here — see loss_utils.py / pointnet2_ops."""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda_f32, require_cuda_i32, stream
+
+
+def _guard(t):
+    return torch.cuda.device(t.device)
+
+
+def nn_pair(adv, ori, both=True):
+    """adv [b,3,n], ori [b,3,m] -> d_a2o [b,n], jstar [b,n] i32, d_o2a [b,m] | None, istar [b,m] | None"""
+    require_cuda_f32(adv, "adv_pc"); require_cuda_f32(ori, "ori_pc")
+    b, c, n = adv.shape
+    m = ori.shape[2]
+    if c != 3 or ori.shape[0] != b or ori.shape[1] != 3:
+        raise RuntimeError("expected [b,3,n] and [b,3,m] clouds")
+    d1 = torch.empty(b, n, device=adv.device, dtype=torch.float32)
+    j1 = torch.empty(b, n, device=adv.device, dtype=torch.int32)
+    d2 = torch.empty(b, m, device=adv.device, dtype=torch.float32) if both else None
+    i2 = torch.empty(b, m, device=adv.device, dtype=torch.int32) if both else None
+    with _guard(adv):
+        check(_lib.load().geoa3_nn_pair(ptr(adv), ptr(ori), b, n, m, ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(adv)))
+    return d1, j1, d2, i2
+
+
+def knn(query, ref, K, drop=0, return_dist=False):
+    """query [b,3,n], ref [b,3,m] -> idx [b,n,K-drop] i32 (ascending (dist,idx)), dist | None"""
+    require_cuda_f32(query, "query"); require_cuda_f32(ref, "ref")
+    b, _, n = query.shape
+    m = ref.shape[2]
+    idx = torch.empty(b, n, K - drop, device=query.device, dtype=torch.int32)
+    dist = torch.empty(b, n, K - drop, device=query.device, dtype=torch.float32) if return_dist else None
+    with _guard(query):
+        check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(idx), ptr(dist), stream(query)))
+    return idx, dist
+
+
+def kappa_loss_fwd(pc, normal=None, jstar=None, nbr=None, d_a2o=None, d_o2a=None, kappa_ori=None, m=None,
+                   want_kappa=True, want_nrm=False, want_cd=False, want_hd=False, want_curv=False):
+    """One launch: kappa / borrowed normals / per-cloud CD, HD(+argmax), curvature loss. Returns a dict."""
+    require_cuda_f32(pc, "pc")
+    b, _, n = pc.shape
+    if m is None:
+        m = normal.shape[2] if normal is not None else (d_o2a.shape[1] if d_o2a is not None else n)
+    k = nbr.shape[2] if nbr is not None else 0
+    dev = pc.device
+    out = {}
+    kap = torch.empty(b, n, device=dev, dtype=torch.float32) if (want_kappa and k > 0) else None
+    nrm = torch.empty(b, 3, n, device=dev, dtype=torch.float32) if (want_nrm and k > 0) else None
+    cd = torch.empty(b, device=dev, dtype=torch.float32) if want_cd else None
+    hd = torch.empty(b, device=dev, dtype=torch.float32) if want_hd else None
+    ha = torch.empty(b, device=dev, dtype=torch.int32) if want_hd else None
+    cu = torch.empty(b, device=dev, dtype=torch.float32) if (want_curv and k > 0) else None
+    with _guard(pc):
+        check(_lib.load().geoa3_kappa_loss_fwd(ptr(pc), ptr(normal), ptr(jstar), ptr(nbr), k, ptr(d_a2o), ptr(d_o2a),
+                                               ptr(kappa_ori), b, n, m, ptr(kap), ptr(nrm), ptr(cd), ptr(hd), ptr(ha),
+                                               ptr(cu), stream(pc)))
+    out.update(kappa=kap, nrm=nrm, cd=cd, hd=hd, hd_arg=ha, curv=cu)
+    return out
+
+
+def loss_bwd(adv, ori=None, nrm_adv=None, kappa_adv=None, kappa_ori=None, jstar=None, istar=None, nbr=None,
+             hd_arg=None, g_cd=None, g_hd=None, g_cu=None, g_kappa=None, m=None):
+    """Fused deterministic backward -> grad_adv [b,3,n]."""
+    require_cuda_f32(adv, "adv_pc")
+    b, _, n = adv.shape
+    if m is None:
+        m = ori.shape[2] if ori is not None else n
+    k = nbr.shape[2] if nbr is not None else 0
+    grad = torch.empty_like(adv)
+    for g in (g_cd, g_hd, g_cu, g_kappa):
+        if g is not None:
+            require_cuda_f32(g, "upstream gradient")
+    with _guard(adv):
+        check(_lib.load().geoa3_loss_bwd(ptr(adv), ptr(ori), ptr(nrm_adv), ptr(kappa_adv), ptr(kappa_ori), ptr(jstar),
+                                         ptr(istar), ptr(nbr), ptr(hd_arg), ptr(g_cd), ptr(g_hd), ptr(g_cu),
+                                         ptr(g_kappa), b, n, m, k, ptr(grad), stream(adv)))
+    return grad
+
+
+# ------------------------------------------------------------------ pointnet2_ops (bindings.cpp:6-19 names)
+def furthest_point_sampling(points, nsamples):
+    require_cuda_f32(points, "points")
+    b, n, _ = points.shape
+    out = torch.empty(b, nsamples, device=points.device, dtype=torch.int32)
+    with _guard(points):
+        check(_lib.load().geoa3_furthest_point_sampling(ptr(points), b, n, nsamples, ptr(out), stream(points)))
+    return out
+
+
+def gather_points(points, idx):
+    require_cuda_f32(points, "points"); require_cuda_i32(idx, "idx")
+    b, c, n = points.shape
+    m = idx.shape[1]
+    out = torch.empty(b, c, m, device=points.device, dtype=torch.float32)
+    with _guard(points):
+        check(_lib.load().geoa3_gather_points(ptr(points), ptr(idx), b, c, n, m, ptr(out), stream(points)))
+    return out
+
+
+def _workspace(dev, b, n, npoints, nsample):
+    nbytes = _lib.load().geoa3_group_points_grad_workspace_bytes(b, n, npoints, nsample)
+    return torch.empty(nbytes, device=dev, dtype=torch.uint8), nbytes
+
+
+def gather_points_grad(grad_out, idx, n):
+    require_cuda_f32(grad_out, "grad_out"); require_cuda_i32(idx, "idx")
+    b, c, m = grad_out.shape
+    out = torch.empty(b, c, n, device=grad_out.device, dtype=torch.float32)
+    ws, nbytes = _workspace(grad_out.device, b, n, m, 1)
+    with _guard(grad_out):
+        check(_lib.load().geoa3_gather_points_grad(ptr(grad_out), ptr(idx), b, c, n, m, ptr(out), ptr(ws), nbytes,
+                                                   stream(grad_out)))
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    require_cuda_f32(new_xyz, "new_xyz"); require_cuda_f32(xyz, "xyz")
+    b, n, _ = xyz.shape
+    m = new_xyz.shape[1]
+    idx = torch.empty(b, m, nsample, device=xyz.device, dtype=torch.int32)
+    with _guard(xyz):
+        check(_lib.load().geoa3_ball_query(ptr(new_xyz), ptr(xyz), b, n, m, float(radius), int(nsample), ptr(idx),
+                                           stream(xyz)))
+    return idx
+
+
+def group_points(points, idx):
+    require_cuda_f32(points, "points"); require_cuda_i32(idx, "idx")
+    b, c, n = points.shape
+    _, npoints, nsample = idx.shape
+    out = torch.empty(b, c, npoints, nsample, device=points.device, dtype=torch.float32)
+    with _guard(points):
+        check(_lib.load().geoa3_group_points(ptr(points), ptr(idx), b, c, n, npoints, nsample, ptr(out), stream(points)))
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    require_cuda_f32(grad_out, "grad_out"); require_cuda_i32(idx, "idx")
+    b, c, npoints, nsample = grad_out.shape
+    out = torch.empty(b, c, n, device=grad_out.device, dtype=torch.float32)
+    ws, nbytes = _workspace(grad_out.device, b, n, npoints, nsample)
+    with _guard(grad_out):
+        check(_lib.load().geoa3_group_points_grad(ptr(grad_out), ptr(idx), b, c, n, npoints, nsample, ptr(out), ptr(ws),
+                                                  nbytes, stream(grad_out)))
+    return out
+
+
+def three_nn(unknowns, knows):
+    require_cuda_f32(unknowns, "unknowns"); require_cuda_f32(knows, "knows")
+    b, n, _ = unknowns.shape
+    m = knows.shape[1]
+    dist2 = torch.empty(b, n, 3, device=unknowns.device, dtype=torch.float32)
+    idx = torch.empty(b, n, 3, device=unknowns.device, dtype=torch.int32)
+    with _guard(unknowns):
+        check(_lib.load().geoa3_three_nn(ptr(unknowns), ptr(knows), b, n, m, ptr(dist2), ptr(idx), stream(unknowns)))
+    return dist2, idx
+
+
+def three_interpolate(points, idx, weight):
+    require_cuda_f32(points, "points"); require_cuda_i32(idx, "idx"); require_cuda_f32(weight, "weight")
+    b, c, m = points.shape
+    n = idx.shape[1]
+    out = torch.empty(b, c, n, device=points.device, dtype=torch.float32)
+    with _guard(points):
+        check(_lib.load().geoa3_three_interpolate(ptr(points), ptr(idx), ptr(weight), b, c, m, n, ptr(out),
+                                                  stream(points)))
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    require_cuda_f32(grad_out, "grad_out"); require_cuda_i32(idx, "idx"); require_cuda_f32(weight, "weight")
+    b, c, n = grad_out.shape
+    out = torch.empty(b, c, m, device=grad_out.device, dtype=torch.float32)
+    ws, nbytes = _workspace(grad_out.device, b, m, n, 3)
+    with _guard(grad_out):
+        check(_lib.load().geoa3_three_interpolate_grad(ptr(grad_out), ptr(idx), ptr(weight), b, c, n, m, ptr(out),
+                                                       ptr(ws), nbytes, stream(grad_out)))
+    return out

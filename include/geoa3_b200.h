@@ -1,0 +1,146 @@
+/*
+ * geoa3_b200.h — C ABI of libgeoa3_b200.so: the B200 (sm_100a) kernels behind GeoA3's
+ * geometry-aware loss path and the pointnet2_ops sampling/grouping ops.
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + int sizes + a CUDA stream handle (cudaStream_t passed as void*);
+ *     no torch types.  The caller allocates every input, output and workspace buffer and keeps
+ *     it alive until the stream has passed the call; the library never allocates user-visible
+ *     memory, never synchronises, and launches on the stream it is given (the reference launches
+ *     on at::cuda::getCurrentCUDAStream(): _ext-src/src/sampling_gpu.cu:25-27,180).
+ *   - return value: 0 = success, >0 = cudaError_t of the launch, <0 = GEOA3_E* argument error.
+ *     Nothing ever calls exit() (the reference does: _ext-src/include/cuda_utils.h:30-39).
+ *   - loss-side clouds are channel-first float32 [b][3][n] (what Lib/loss_utils.py receives);
+ *     pointnet2-side coordinates are AoS float32 [b][n][3] and features [b][c][n]
+ *     (the pointnet2_ops convention); every index tensor is int32.
+ *   - index outputs are bit-exact w.r.t. the pinned arithmetic d = fma(dz,dz,fma(dy,dy,dx*dx)),
+ *     ties -> lowest index; reductions are fixed-order (run-to-run deterministic, no float atomics).
+ *
+ * Paths are relative to the reference checkout (Gorilla-Lab-SCUT/GeoA3).
+ */
+#ifndef GEOA3_B200_H_
+#define GEOA3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEOA3_OK 0
+#define GEOA3_EINVAL (-1)       /* null pointer / non-positive size */
+#define GEOA3_EUNSUPPORTED (-2) /* size outside what the kernels are built for (e.g. K > 33) */
+#define GEOA3_EWORKSPACE (-3)   /* workspace too small */
+
+#define GEOA3_KNN_MAX_K 33 /* K = k+1 <= 33 (curv_loss_knn <= 32, BASELINE config 4) */
+
+typedef void *geoa3_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define GEOA3_API __attribute__((visibility("default")))
+#else
+#define GEOA3_API
+#endif
+
+/* ABI version (major*1000+minor) and error text for any return code. */
+GEOA3_API int geoa3_version(void);
+GEOA3_API const char *geoa3_error_string(int code);
+
+/* ----------------------------------------------------------------------------------------------
+ * Loss path  (replaces pytorch3d.ops.knn_points/knn_gather as used by Lib/loss_utils.py:28-97)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Fused bidirectional 1-NN between adv [b][3][n] and ori [b][3][m]: the N x M distance matrix is
+ * tiled through shared memory and never written.  d_a2o[b][n]/jstar[b][n] = min_j / argmin_j
+ * d(adv_i, ori_j); d_o2a[b][m]/istar[b][m] the other direction (pass NULL for both to skip it:
+ * pseudo_chamfer_loss, hausdorff_loss, find_offset).
+ * Replaces: knn_points(adv, ori, K=1) + knn_points(ori, adv, K=1), Lib/loss_utils.py:32-33,41,48,70,92;
+ *           Attacker/geoA3_attack.py:65,80. */
+GEOA3_API int geoa3_nn_pair(const float *adv, const float *ori, int b, int n, int m, float *d_a2o, int32_t *jstar,
+                  float *d_o2a, int32_t *istar, geoa3_stream_t stream);
+
+/* K nearest of every query [b][3][n] among ref [b][3][m], ascending (dist, idx); the first `drop`
+ * columns are discarded (drop=1 removes the self match exactly like "[:,:,:,1:]").
+ * idx [b][n][K-drop] int32, dist (nullable) [b][n][K-drop].  K <= GEOA3_KNN_MAX_K, K <= m.
+ * Replaces: knn_points(pc, pc, K=k+1).idx[..., 1:], Lib/loss_utils.py:57-58,77-78,139,174. */
+GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int m, int K, int drop, int32_t *idx,
+              float *dist, geoa3_stream_t stream);
+
+/* Local curvature + per-cloud loss reductions, one CTA per cloud, fixed-order reductions.
+ *   kappa_i = (1/k) sum_m |<nrm_i, v_im/max(|v_im|,1e-12)>|,  v_im = pc[nbr[i][m]] - pc[i]
+ *   nrm_i   = normal[:, jstar[i]]  (jstar != NULL: _get_kappa_adv)  or normal[:, i] (jstar NULL: _get_kappa_ori)
+ * pc [b][3][n]; normal [b][3][m], kappa_ori [b][m], d_o2a [b][m] live on the m original points
+ * (jstar NULL requires m == n).  Optional outputs (NULL to skip): kappa [b][n], nrm_out [b][3][n],
+ *   cd[b] = mean d_a2o + mean d_o2a (d_o2a NULL -> one-sided), hd[b] = max d_a2o, hd_arg[b] (lowest i),
+ *   curv[b] = mean (kappa_i - kappa_ori[jstar[i]])^2.   nbr NULL / k 0 skips the curvature part.
+ * Replaces: Lib/loss_utils.py:34,42,49,59-62,71,79-82,93-95; Lib/utility.py:30-31. */
+GEOA3_API int geoa3_kappa_loss_fwd(const float *pc, const float *normal, const int32_t *jstar, const int32_t *nbr, int k,
+                         const float *d_a2o, const float *d_o2a, const float *kappa_ori, int b, int n, int m,
+                         float *kappa, float *nrm_out, float *cd, float *hd, int32_t *hd_arg, float *curv,
+                         geoa3_stream_t stream);
+
+/* Backward of  sum_b (g_cd*CD + g_hd*HD + g_cu*CUR) + sum_{b,i} g_kappa*kappa  w.r.t. adv, in one
+ * kernel: contributions are gathered per target point through CSR lists built in shared memory from
+ * istar / nbr (ascending source order) — deterministic, no float atomics.
+ * Any of g_cd/g_hd/g_cu [b] and g_kappa [b][n] may be NULL (term skipped); istar NULL = one-sided CD.
+ * grad_adv [b][3][n] is fully overwritten.
+ * Replaces: autograd through pytorch3d _knn_points.backward + knn_gather scatter_add (float atomics),
+ *           reached from Attacker/geoA3_attack.py:326. */
+GEOA3_API int geoa3_loss_bwd(const float *adv, const float *ori, const float *nrm_adv, const float *kappa_adv,
+                   const float *kappa_ori, const int32_t *jstar, const int32_t *istar, const int32_t *nbr,
+                   const int32_t *hd_arg, const float *g_cd, const float *g_hd, const float *g_cu,
+                   const float *g_kappa, int b, int n, int m, int k, float *grad_adv, geoa3_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * pointnet2_ops  (replaces the 9 functions exported by _ext-src/src/bindings.cpp:6-19)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* xyz [b][n][3] -> idx [b][m]; same selection (origin skip, 1e10 init, (k mod BS,k) tie order) as
+ * furthest_point_sampling (sampling.cpp:66-87, sampling_gpu.cu:69-229).  No temp buffer needed. */
+GEOA3_API int geoa3_furthest_point_sampling(const float *xyz, int b, int n, int m, int32_t *idx, geoa3_stream_t stream);
+
+/* points [b][c][n], idx [b][m] -> out [b][c][m]        (gather_points, sampling.cpp:15-39) */
+GEOA3_API int geoa3_gather_points(const float *points, const int32_t *idx, int b, int c, int n, int m, float *out,
+                        geoa3_stream_t stream);
+/* grad_out [b][c][m], idx [b][m] -> grad_points [b][c][n] (overwritten; duplicates summed in
+ * ascending j; workspace of geoa3_group_points_grad_workspace_bytes(b, n, m, 1) bytes)
+ *                                                       (gather_points_grad, sampling.cpp:41-65) */
+GEOA3_API int geoa3_gather_points_grad(const float *grad_out, const int32_t *idx, int b, int c, int n, int m,
+                             float *grad_points, void *workspace, size_t workspace_bytes,
+                             geoa3_stream_t stream);
+
+/* new_xyz [b][m][3], xyz [b][n][3] -> idx [b][m][nsample] (ball_query, ball_query.cpp:8-32,
+ * ball_query_gpu.cu:9-54: first nsample hits in index order, d2 < r*r strict, first-hit fill,
+ * no hit -> zeros). */
+GEOA3_API int geoa3_ball_query(const float *new_xyz, const float *xyz, int b, int n, int m, float radius, int nsample,
+                     int32_t *idx, geoa3_stream_t stream);
+
+/* points [b][c][n], idx [b][npoints][nsample] -> out [b][c][npoints][nsample]
+ *                                                       (group_points, group_points.cpp:12-36) */
+GEOA3_API int geoa3_group_points(const float *points, const int32_t *idx, int b, int c, int n, int npoints, int nsample,
+                       float *out, geoa3_stream_t stream);
+/* Deterministic scatter: a CSR-by-target of idx is built once into `workspace` (size from
+ * geoa3_group_points_grad_workspace_bytes) and shared by all c channels; sums in ascending (j,k).
+ * grad_points [b][c][n] is fully overwritten.           (group_points_grad, group_points.cpp:38-62) */
+GEOA3_API size_t geoa3_group_points_grad_workspace_bytes(int b, int n, int npoints, int nsample);
+GEOA3_API int geoa3_group_points_grad(const float *grad_out, const int32_t *idx, int b, int c, int n, int npoints,
+                            int nsample, float *grad_points, void *workspace, size_t workspace_bytes,
+                            geoa3_stream_t stream);
+
+/* unknown [b][n][3], known [b][m][3] -> dist2 [b][n][3], idx [b][n][3]   (three_nn, interpolate.cpp) */
+GEOA3_API int geoa3_three_nn(const float *unknown, const float *known, int b, int n, int m, float *dist2, int32_t *idx,
+                   geoa3_stream_t stream);
+/* points [b][c][m], idx/weight [b][n][3] -> out [b][c][n]               (three_interpolate) */
+GEOA3_API int geoa3_three_interpolate(const float *points, const int32_t *idx, const float *weight, int b, int c, int m,
+                            int n, float *out, geoa3_stream_t stream);
+/* grad_out [b][c][n] -> grad_points [b][c][m] (overwritten, deterministic; workspace of
+ * geoa3_group_points_grad_workspace_bytes(b, m, n, 3) bytes)             (three_interpolate_grad) */
+GEOA3_API int geoa3_three_interpolate_grad(const float *grad_out, const int32_t *idx, const float *weight, int b, int c,
+                                 int n, int m, float *grad_points, void *workspace, size_t workspace_bytes,
+                                 geoa3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOA3_B200_H_ */

@@ -1,0 +1,46 @@
+"""Generates tests/golden/loss_*.npz by running the REFERENCE's own Lib/loss_utils.py (verbatim, from
+/root/reference, with its un-vendored pytorch3d dependency stubbed as documented in
+oracle/ref_loader.py).  Run in the build container only:  python tests/golden/make_golden.py
+
+Each fixture holds fp32 inputs (adv, ori, normal), the reference's fp32 outputs and autograd gradient of
+sum_b(CD + 0.1*HD + CUR) (weights of main_attack.py:342-349), plus an fp64 run of the same reference code
+for tight value checks.  Index tensors are not stored: the reference API does not return them; index parity
+is pinned by oracle/geoa3_oracle.c (see its header)."""
+import os.path as osp
+import sys
+
+import numpy as np
+import torch
+
+ROOT = osp.dirname(osp.dirname(osp.dirname(osp.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader, synth  # noqa: E402
+
+HERE = osp.dirname(osp.abspath(__file__))
+CASES = [
+    # name, b, n, k, offset std, first instance
+    ("loss_b3_n256_k16", 3, 256, 16, 2e-2, 0),
+    ("loss_b2_n500_k8", 2, 500, 8, 1e-3, 3),     # ragged n, reference-sized initial perturbation
+    ("loss_b4_n128_k16_big", 4, 128, 16, 1e-1, 6),  # large perturbation: many-to-one argmins, empty columns
+]
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    for name, b, n, k, std, start in CASES:
+        pc, nr, lab = synth.make_batch(b, n, start)
+        adv = pc + synth.make_offsets(b, n, seed=7 + start, std=std)
+        r32 = ref_loader.geo_loss_and_grad(adv, pc, nr, k, dtype=torch.float32)
+        r64 = ref_loader.geo_loss_and_grad(adv, pc, nr, k, dtype=torch.float64)
+        out = dict(adv=adv, ori=pc, normal=nr, k=np.int32(k))
+        for key, v in r32.items():
+            out["f32_" + key] = v
+        for key, v in r64.items():
+            out["f64_" + key] = v
+        np.savez_compressed(osp.join(HERE, name + ".npz"), **out)
+        print(name, "cd", r32["cd"], "hd", r32["hd"], "curv", r32["curv"])
+
+
+if __name__ == "__main__":
+    main()

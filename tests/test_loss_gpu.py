@@ -1,0 +1,202 @@
+"""GPU parity (-m gpu): the CUDA loss path, called through the C ABI (geoa3_b200.ops / loss_utils),
+against the CPU oracle on the same seeded inputs and against the committed reference golden vectors.
+Indices bit-exact; values / gradients within 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_files, rel_err
+from oracle import oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make(b, n, start=0, std=1e-2, seed=1):
+    pc, nr, _ = synth.make_batch(b, n, start)
+    adv = pc + synth.make_offsets(b, n, seed=seed, std=std)
+    return adv, pc, nr
+
+
+@pytest.mark.parametrize("b,n,m,std", [(4, 1024, 1024, 1e-3), (3, 1000, 1000, 5e-2), (2, 333, 777, 1e-1),
+                                       (1, 2500, 2049, 1e-2), (5, 7, 3, 1.0)])
+def test_nn_pair_bitexact(b, n, m, std):
+    from geoa3_b200 import ops
+
+    adv, _, _ = make(b, n, 0, std)
+    _, ori, _ = make(b, m, 3, std)
+    d1, j1, d2, i2 = ops.nn_pair(cu(adv), cu(ori))
+    od1, oj1 = O.nn1(adv, ori)
+    od2, oi2 = O.nn1(ori, adv)
+    assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)  # bit-exact fp32
+    d1b, j1b, none_d, none_i = ops.nn_pair(cu(adv), cu(ori), both=False)
+    assert none_d is None and np.array_equal(j1b.cpu().numpy(), oj1)
+
+
+def test_nn_pair_ties_lowest_index():
+    from geoa3_b200 import ops
+
+    pc, _ = synth.lattice_cloud(216)
+    a = np.stack([pc, pc[:, ::-1].copy()])
+    o = np.stack([pc + 0.125, pc])  # half-cell shift: 8 equidistant corners per query
+    d1, j1, d2, i2 = ops.nn_pair(cu(a), cu(o))
+    od1, oj1 = O.nn1(a, o)
+    od2, oi2 = O.nn1(o, a)
+    assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1)
+
+
+@pytest.mark.parametrize("b,n,K", [(3, 1024, 17), (2, 1024, 33), (2, 1000, 17), (2, 515, 3), (1, 4096, 17),
+                                   (2, 300, 6), (1, 40, 33)])
+def test_knn_bitexact(b, n, K):
+    from geoa3_b200 import ops
+
+    adv, _, _ = make(b, n, 2, 2e-2)
+    idx, dist = ops.knn(cu(adv), cu(adv), K, drop=0, return_dist=True)
+    oi, od = O.knn(adv, adv, K)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    assert np.array_equal(dist.cpu().numpy(), od)
+    idx1, _ = ops.knn(cu(adv), cu(adv), K, drop=1)
+    assert np.array_equal(idx1.cpu().numpy(), oi[:, :, 1:])
+
+
+def test_knn_ties_lexicographic():
+    from geoa3_b200 import ops
+
+    pc, _ = synth.lattice_cloud(343)
+    pc = np.stack([pc, pc * 0.5])
+    for K in (9, 17, 33):
+        idx, dist = ops.knn(cu(pc), cu(pc), K, return_dist=True)
+        oi, od = O.knn(pc, pc, K)
+        assert np.array_equal(idx.cpu().numpy(), oi), K
+    # duplicated points: zero distances, self is not necessarily column 0
+    dup = np.concatenate([pc[:, :, :50], pc[:, :, :50], pc[:, :, 50:100]], 2)
+    idx, _ = ops.knn(cu(dup), cu(dup), 5)
+    assert np.array_equal(idx.cpu().numpy(), O.knn(dup, dup, 5)[0])
+
+
+@pytest.mark.parametrize("b,n,k,std", [(4, 1024, 16, 1e-3), (3, 1000, 16, 3e-2), (2, 512, 32, 1e-2), (2, 200, 2, 1e-1)])
+def test_fused_forward_backward_vs_oracle(b, n, k, std):
+    from geoa3_b200 import loss_utils as L
+
+    adv, ori, nrm = make(b, n, 5, std)
+    kap_ori_o, nbr_o = O.kappa_ori(ori, nrm, k)
+    ko = L._get_kappa_ori(cu(ori), cu(nrm), k)
+    assert rel_err(ko.cpu().numpy(), kap_ori_o) < TOL
+    ko32 = ko.cpu().numpy()
+    fwd = O.geo_forward(adv, ori, nrm, ko32, k)
+
+    a = cu(adv).requires_grad_(True)
+    scale = torch.linspace(0.5, 2.0, b, device="cuda")
+    total, cd, hd, cv = L.geo_loss(a, cu(ori), cu(nrm), ko, k, 1.0, 0.1, 1.0)
+    for name, got in (("cd", cd), ("hd", hd), ("curv", cv)):
+        assert rel_err(got.cpu().numpy(), fwd[name]) < TOL, name
+    (total * scale).sum().backward()
+    s = scale.cpu().numpy().astype(np.float64)
+    G = O.geo_backward(adv, ori, fwd, ko32, s * 1.0, s * 0.1, s * 1.0)
+    assert rel_err(a.grad.cpu().numpy(), G) < TOL
+    # per-cloud check too (a big cloud must not hide a bad small one)
+    for c in range(b):
+        assert rel_err(a.grad[c].cpu().numpy(), G[c]) < 5 * TOL
+
+
+def test_backward_is_deterministic():
+    from geoa3_b200 import loss_utils as L
+
+    adv, ori, nrm = make(6, 1024, 9, 2e-2)
+    ko = L._get_kappa_ori(cu(ori), cu(nrm), 16)
+    grads = []
+    for _ in range(3):
+        L.clear_cache()
+        a = cu(adv).requires_grad_(True)
+        L.geo_loss(a, cu(ori), cu(nrm), ko, 16)[0].sum().backward()
+        grads.append(a.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+
+
+@pytest.mark.parametrize("path", golden_files())
+def test_reference_api_vs_golden(path):
+    """The reference-named functions composed exactly as Attacker/geoA3_attack.py:131-162 does."""
+    from geoa3_b200 import loss_utils as L
+
+    g = np.load(path)
+    k = int(g["k"])
+    L.clear_cache()
+    adv = cu(g["adv"]).requires_grad_(True)
+    ori, nrm = cu(g["ori"]), cu(g["normal"])
+    kap_ori = L._get_kappa_ori(ori, nrm, k)
+    cd = L.chamfer_loss(adv, ori)
+    hd = L.hausdorff_loss(adv, ori)
+    kap_adv, nrm_adv = L._get_kappa_adv(adv, ori, nrm, k)
+    cu_ = L.curvature_loss(adv, ori, kap_adv, kap_ori)
+    (1.0 * cd + 0.1 * hd + 1.0 * cu_).sum().backward()
+    assert rel_err(kap_ori.detach().cpu().numpy(), g["f64_kappa_ori"]) < TOL
+    assert rel_err(kap_adv.detach().cpu().numpy(), g["f64_kappa_adv"]) < TOL
+    assert np.array_equal(nrm_adv.cpu().numpy(), g["f32_nrm_adv"])
+    for name, got in (("cd", cd), ("hd", hd), ("curv", cu_)):
+        assert rel_err(got.detach().cpu().numpy(), g["f64_" + name]) < TOL, name
+    assert rel_err(adv.grad.cpu().numpy(), g["f64_grad"]) < TOL
+    # fused path gives the same numbers
+    L.clear_cache()
+    adv2 = cu(g["adv"]).requires_grad_(True)
+    tot, cd2, hd2, cv2 = L.geo_loss(adv2, ori, nrm, kap_ori.detach(), k, 1.0, 0.1, 1.0)
+    tot.sum().backward()
+    assert rel_err(adv2.grad.cpu().numpy(), g["f64_grad"]) < TOL
+    assert rel_err(cd2.cpu().numpy(), g["f64_cd"]) < TOL
+    # one-sided chamfer (pseudo_chamfer_loss) value + grad vs oracle
+    L.clear_cache()
+    adv3 = cu(g["adv"]).requires_grad_(True)
+    pc = L.pseudo_chamfer_loss(adv3, ori)
+    pc.sum().backward()
+    d1, j1 = O.nn1(g["adv"], g["ori"])
+    assert rel_err(pc.detach().cpu().numpy(), d1.astype(np.float64).mean(1)) < TOL
+    n = g["adv"].shape[2]
+    Gp = 2.0 / n * (g["adv"].astype(np.float64) - np.take_along_axis(g["ori"].astype(np.float64), j1[:, None, :].repeat(3, 1), 2))
+    assert rel_err(adv3.grad.cpu().numpy(), Gp) < TOL
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (B=250, N=1024): size-independent properties instead of an oracle sweep."""
+    from geoa3_b200 import loss_utils as L
+    from geoa3_b200 import ops
+
+    b, n = 250, 1024
+    pc, nr, _ = synth.make_batch(10, n, 0)
+    reps = b // 10
+    ori = np.tile(pc, (reps, 1, 1))
+    nrm = np.tile(nr, (reps, 1, 1))
+    adv = ori + synth.make_offsets(b, n, seed=0, std=1e-3)
+    A, Oc = cu(adv), cu(ori)
+    d1, j1, d2, i2 = ops.nn_pair(A, Oc)
+    # tiny perturbation: every adv point's nearest original is its own source point (and vice versa)
+    ar = torch.arange(n, device="cuda", dtype=torch.int32)[None].expand(b, n)
+    assert (j1 == ar).float().mean() > 0.99 and (i2 == ar).float().mean() > 0.99
+    # d1 is really the distance to the reported argmin
+    gath = torch.gather(Oc, 2, j1.long()[:, None, :].expand(b, 3, n))
+    assert torch.allclose(((A - gath) ** 2).sum(1), d1, rtol=1e-5, atol=1e-12)
+    # self-kNN: first column is the point itself, distances ascending
+    idx, dist = ops.knn(A, A, 17, return_dist=True)
+    assert torch.equal(idx[:, :, 0], ar) and bool((dist[:, :, 1:] >= dist[:, :, :-1]).all())
+    # spot-check 3 clouds against the oracle
+    sel = [0, 123, 249]
+    oi, _ = O.knn(adv[sel], adv[sel], 17)
+    assert np.array_equal(idx[sel].cpu().numpy(), oi)
+    # identical clouds (replicas) give identical losses/gradients: batch independence
+    ko = L._get_kappa_ori(Oc, cu(nrm), 16)
+    a = A.clone().requires_grad_(True)
+    tot, cd, hd, cv = L.geo_loss(a, Oc, cu(nrm), ko, 16)
+    tot.sum().backward()
+    assert torch.equal(ko[:10], ko[10:20])
+    a2 = A[:20].clone().requires_grad_(True)
+    L.geo_loss(a2, Oc[:20].contiguous(), cu(nrm[:20]), ko[:20].contiguous(), 16)[0].sum().backward()
+    assert torch.equal(a.grad[:20], a2.grad)
+    # zero perturbation: CD = HD = 0 and the Chamfer/Hausdorff gradient vanishes
+    z = Oc.clone().requires_grad_(True)
+    (L.chamfer_loss(z, Oc) + L.hausdorff_loss(z, Oc)).sum().backward()
+    assert float(z.grad.abs().max()) == 0.0

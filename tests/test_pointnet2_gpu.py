@@ -1,0 +1,155 @@
+"""GPU parity (-m gpu) of the pointnet2_ops drop-in against the CPU oracle and, when the prebuilt
+oracle/_ref/pointnet2_ref_ext.so travelled to the box, against the reference's own CUDA kernels."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def clouds(b, n, start=0):
+    pc, _, _ = synth.make_batch(b, n, start)
+    return np.ascontiguousarray(pc.transpose(0, 2, 1))  # (b,n,3)
+
+
+def ref_ext():
+    from oracle import build_ref
+
+    return build_ref.load_ref()
+
+
+@pytest.mark.parametrize("b,n,m", [(10, 1024, 512), (10, 512, 128), (3, 1000, 100), (2, 37, 37), (2, 2048, 64),
+                                   (1, 5000, 32)])
+def test_fps_bitexact(b, n, m):
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    xyz = clouds(b, n)  # family 6 (flat plate) has points inside the |p|^2<=1e-3 skip zone
+    got = pu.furthest_point_sample(cu(xyz), m)
+    assert got.dtype == torch.int32 and not got.requires_grad
+    assert np.array_equal(got.cpu().numpy(), O.fps(xyz, m))
+    ext = ref_ext()
+    if ext is not None:
+        assert torch.equal(got, ext.furthest_point_sampling(cu(xyz), m))
+
+
+def test_fps_ties_and_degenerate():
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    lat, _ = synth.lattice_cloud(216)
+    xyz = np.ascontiguousarray(lat.T[None])
+    zeros = np.full((1, 64, 3), 1e-3, np.float32)
+    for x, m in ((xyz, 100), (zeros, 10), (np.tile(xyz, (1, 3, 1)), 50)):
+        got = pu.furthest_point_sample(cu(x), m).cpu().numpy()
+        assert np.array_equal(got, O.fps(x, m))
+        ext = ref_ext()
+        if ext is not None:
+            assert np.array_equal(got, ext.furthest_point_sampling(cu(x), m).cpu().numpy())
+
+
+@pytest.mark.parametrize("b,n,m,r,ns", [(10, 1024, 512, 0.2, 64), (10, 512, 128, 0.4, 64), (4, 1024, 512, 0.1, 16),
+                                        (4, 1024, 512, 0.4, 128), (2, 999, 77, 0.3, 33), (2, 100, 10, 0.01, 8)])
+def test_ball_query_bitexact(b, n, m, r, ns):
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    xyz = clouds(b, n, 1)
+    new = np.ascontiguousarray(xyz[:, O.fps(xyz, m)[0], :]) if b == 1 else np.stack(
+        [xyz[i, O.fps(xyz[i:i + 1], m)[0]] for i in range(b)])
+    new[:, -1] += 7.0  # a centroid with no neighbour at all -> all-zero row
+    got = pu.ball_query(r, ns, cu(xyz), cu(new))
+    assert got.dtype == torch.int32 and got.shape == (b, m, ns)
+    assert np.array_equal(got.cpu().numpy(), O.ball_query(new, xyz, r, ns))
+    ext = ref_ext()
+    if ext is not None:
+        assert torch.equal(got, ext.ball_query(cu(new), cu(xyz), r, ns))
+
+
+@pytest.mark.parametrize("b,c,n,m,ns", [(4, 3, 1024, 512, 64), (4, 128, 512, 128, 64), (2, 67, 300, 50, 7),
+                                        (2, 320, 512, 128, 128)])
+def test_group_points_and_grad(b, c, n, m, ns):
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(0)
+    xyz = clouds(b, n, 2)
+    new = np.stack([xyz[i, O.fps(xyz[i:i + 1], m)[0]] for i in range(b)])
+    idx = O.ball_query(new, xyz, 0.3, ns)
+    feats = rng.standard_normal((b, c, n)).astype(np.float32)
+    f = cu(feats).requires_grad_(True)
+    out = pu.grouping_operation(f, cu(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), O.group_points(feats, idx))
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(cu(go))
+    ref = O.group_points_grad(go, idx, n)
+    assert rel_err(f.grad.cpu().numpy(), ref) < 1e-5
+    # deterministic: bitwise equal on a second run
+    f2 = cu(feats).requires_grad_(True)
+    pu.grouping_operation(f2, cu(idx)).backward(cu(go))
+    assert torch.equal(f.grad, f2.grad)
+    ext = ref_ext()
+    if ext is not None:
+        assert torch.equal(out.detach(), ext.group_points(cu(feats), cu(idx)))
+        assert rel_err(f.grad.cpu().numpy(), ext.group_points_grad(cu(go), cu(idx), n).cpu().numpy()) < 1e-5
+
+
+def test_gather_and_grad():
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(1)
+    b, c, n, m = 5, 3, 1024, 512
+    feats = rng.standard_normal((b, c, n)).astype(np.float32)
+    idx = rng.integers(0, n, (b, m)).astype(np.int32)
+    idx[:, :5] = 7  # duplicates
+    f = cu(feats).requires_grad_(True)
+    out = pu.gather_operation(f, cu(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), O.gather_points(feats, idx))
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(cu(go))
+    assert rel_err(f.grad.cpu().numpy(), O.gather_points_grad(go, idx, n)) < 1e-6
+
+
+def test_three_nn_interpolate():
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(2)
+    b, n, m, c = 3, 700, 190, 19
+    unknown = clouds(b, n, 4)
+    known = clouds(b, m, 5)
+    dist, idx = pu.three_nn(cu(unknown), cu(known))
+    od, oi = O.three_nn(unknown, known)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(od))
+    w = rng.uniform(size=(b, n, 3)).astype(np.float32)
+    pts = rng.standard_normal((b, c, m)).astype(np.float32)
+    p = cu(pts).requires_grad_(True)
+    out = pu.three_interpolate(p, idx, cu(w))
+    assert rel_err(out.detach().cpu().numpy(), O.three_interpolate(pts, oi, w)) < 1e-6
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(cu(go))
+    assert rel_err(p.grad.cpu().numpy(), O.three_interpolate_grad(go, oi, w, m)) < 1e-5
+    ext = ref_ext()
+    if ext is not None:
+        rd, ri = ext.three_nn(cu(unknown), cu(known))
+        assert torch.equal(ri, idx) and torch.equal(torch.sqrt(rd), dist)
+
+
+def test_query_and_group_module():
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    xyz = clouds(2, 256, 3)
+    X = cu(xyz)
+    fidx = pu.furthest_point_sample(X, 32)
+    new_xyz = pu.gather_operation(X.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+    feats = torch.randn(2, 5, 256, device="cuda")
+    out = pu.QueryAndGroup(0.3, 16, use_xyz=True)(X, new_xyz, feats)
+    assert out.shape == (2, 8, 32, 16)
+    idx = O.ball_query(new_xyz.cpu().numpy(), xyz, 0.3, 16)
+    gx = O.group_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx) - new_xyz.cpu().numpy().transpose(0, 2, 1)[..., None]
+    assert np.allclose(out[:, :3].cpu().numpy(), gx, atol=0, rtol=0)
+    assert pu.GroupAll()(X, None, feats).shape == (2, 8, 1, 256)
