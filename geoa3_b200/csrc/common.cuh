@@ -41,6 +41,26 @@ __device__ __forceinline__ float2 dist2x2(float2 cx, float2 cy, float2 cz, float
   return t;
 }
 
+// The pointnet2_ops kernels of the reference were written as (dx*dx) + (dy*dy) + (dz*dz); nvcc's fma
+// contraction turns that into  t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)  (verified in the SASS of
+// the reference built for sm_100: FPS, ball_query and three_nn all start from the y term).  Index parity
+// with the reference binary needs exactly this order, which differs from the kNN loop above in the last ulp.
+__device__ __forceinline__ float dist2_pn2(float px, float py, float pz, float qx, float qy, float qz) {
+  float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+  float t = __fmul_rn(dy, dy);
+  t = __fmaf_rn(dx, dx, t);
+  t = __fmaf_rn(dz, dz, t);
+  return t;
+}
+
+__device__ __forceinline__ float2 dist2x2_pn2(float2 cx, float2 cy, float2 cz, float2 nqx, float2 nqy, float2 nqz) {
+  float2 dx = __fadd2_rn(cx, nqx), dy = __fadd2_rn(cy, nqy), dz = __fadd2_rn(cz, nqz);
+  float2 t = __fmul2_rn(dy, dy);
+  t = __ffma2_rn(dx, dx, t);
+  t = __ffma2_rn(dz, dz, t);
+  return t;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,8 +6,10 @@
 //    the last selected point.  One round = P fused distance updates + a 2-instruction warp arg-max
 //    (REDUX on the packed key) + ONE block barrier (double-buffered partials), instead of the
 //    reference's 10 barriers and global-memory temp round trip.  The selection order of the reference
-//    (max distance, ties -> smallest (k mod BS, k), points with |p|^2 <= 1e-3 never touched) is encoded
-//    in a 64-bit sort key so any thread layout reproduces it bit for bit.
+//    (max distance; ties -> the point whose reference thread id k mod BS is smallest in BIT-REVERSED
+//    order — that is what its shared-memory tournament with "lower slot keeps ties" does — then the
+//    smallest k; points with |p|^2 <= 1e-3 never touched) is encoded in a 64-bit sort key so any thread
+//    layout reproduces it bit for bit.
 //  * ball query runs a warp per centroid: 64 candidates per step on the packed fp32 pipe, ballots give
 //    the in-order write positions, the scan stops as soon as nsample hits are found.
 //  * group_points stages the gathered rows in shared memory (random 4-byte global gathers would cost a
@@ -30,7 +32,7 @@ static int ref_fps_block(int n) {
 
 template <int P>
 __global__ void __launch_bounds__(1024)
-fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int32_t* __restrict__ idxs) {
+fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs) {
   extern __shared__ __align__(16) float s_xyz[];  // [3][n] SoA mirror of the cloud
   __shared__ unsigned long long s_part[2][FPS_MAX_WARPS];
 
@@ -50,8 +52,12 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int32_t* __r
     if (k < n) {
       px[t] = p[k * 3]; py[t] = p[k * 3 + 1]; pz[t] = p[k * 3 + 2];
       s_xyz[k] = px[t]; s_xyz[n + k] = py[t]; s_xyz[2 * n + k] = pz[t];
-      const float mag = __fmaf_rn(pz[t], pz[t], __fmaf_rn(py[t], py[t], __fmul_rn(px[t], px[t])));
-      if (!((double)mag <= 1e-3)) tk[t] = ~(((unsigned)(k % ref_bs) << 20) | (unsigned)k);
+      const float mag = __fmaf_rn(pz[t], pz[t], __fmaf_rn(px[t], px[t], __fmul_rn(py[t], py[t])));  // y,x,z (SASS)
+      // reference tournament (sampling_gpu.cu:115-168): at stride s slot t keeps ties against slot t+s, so
+      // among equal distances the winner has the smallest bit-reversed thread id; inside one reference
+      // thread (k = tid, tid+BS, ...) the strict '>' keeps the smallest k.
+      const unsigned rtid = ref_bits ? (__brev((unsigned)(k % ref_bs)) >> (32 - ref_bits)) : 0u;
+      if (!((double)mag <= 1e-3)) tk[t] = ~((rtid << 20) | (unsigned)k);
     }
   }
   if (tid == 0) out[0] = 0;
@@ -64,7 +70,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int32_t* __r
 #pragma unroll
     for (int t = 0; t < P; ++t) {
       if (tk[t] != 0u) {
-        const float d = dist2(px[t], py[t], pz[t], x1, y1, z1);
+        const float d = dist2_pn2(px[t], py[t], pz[t], x1, y1, z1);
         temp[t] = fminf(d, temp[t]);
         const unsigned h = __float_as_uint(temp[t]);
         if (h > bh || (h == bh && tk[t] > bl)) { bh = h; bl = tk[t]; }
@@ -118,8 +124,8 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
     int cnt = 0;
     for (int j0 = 0; j0 < n64 && cnt < nsample; j0 += 64) {
       const int ja = j0 + lane, jb = j0 + 32 + lane;
-      const float2 d = dist2x2(make_float2(sx[ja], sx[jb]), make_float2(sy[ja], sy[jb]), make_float2(sz[ja], sz[jb]),
-                               nqx, nqy, nqz);
+      const float2 d = dist2x2_pn2(make_float2(sx[ja], sx[jb]), make_float2(sy[ja], sy[jb]),
+                                   make_float2(sz[ja], sz[jb]), nqx, nqy, nqz);
       const bool ha = d.x < r2, hb = d.y < r2;
       const unsigned ba = __ballot_sync(0xffffffffu, ha), bb = __ballot_sync(0xffffffffu, hb);
       const int pa = cnt + __popc(ba & lt);
@@ -288,7 +294,7 @@ three_nn_kernel(const float* __restrict__ unknown, const float* __restrict__ kno
     }
     __syncthreads();
     for (int t = 0; t < cn; ++t) {
-      const float d = dist2(ux, uy, uz, sx[t], sy[t], sz[t]);
+      const float d = dist2_pn2(ux, uy, uz, sx[t], sy[t], sz[t]);
       const int k = c0 + t;
       if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
       else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
@@ -311,9 +317,10 @@ __global__ void three_interpolate_kernel(const float* __restrict__ points, const
   if (j >= n) return;
   const size_t o = ((size_t)cloud * n + j) * 3;
   const float* p = points + ((size_t)cloud * c + ch) * m;
-  // same expression shape as interpolate_gpu.cu:98-99 (mul, fma, fma under default contraction)
+  // interpolate_gpu.cu:98-99 `p1*w1 + p2*w2 + p3*w3` is contracted by nvcc into
+  // t = p2*w2; t = fma(p1,w1,t); t = fma(p3,w3,t)  (read off the reference SASS) — reproduced exactly.
   out[((size_t)cloud * c + ch) * n + j] =
-      __fmaf_rn(p[idx[o + 2]], weight[o + 2], __fmaf_rn(p[idx[o + 1]], weight[o + 1], __fmul_rn(p[idx[o]], weight[o])));
+      __fmaf_rn(p[idx[o + 2]], weight[o + 2], __fmaf_rn(p[idx[o]], weight[o], __fmul_rn(p[idx[o + 1]], weight[o + 1])));
 }
 
 static size_t csr_ws_bytes(int b, int n, int E) { return (size_t)b * ((size_t)n + 1 + (size_t)E) * sizeof(int); }
@@ -363,6 +370,8 @@ extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = (size_t)n * 12;
   const int bs = ref_fps_block(n);
+  int bits = 0;
+  while ((1 << bits) < bs) ++bits;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(fps_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -373,11 +382,11 @@ extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int
   }
   if (n <= 4096) {
     const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
-    fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, idx);
+    fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx);
   } else if (n <= 8192) {
-    fps_kernel<8><<<b, 1024, smem, s>>>(xyz, n, m, bs, idx);
+    fps_kernel<8><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx);
   } else if (n <= 16384) {
-    fps_kernel<16><<<b, 1024, smem, s>>>(xyz, n, m, bs, idx);
+    fps_kernel<16><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx);
   } else {
     return GEOA3_EUNSUPPORTED;
   }

@@ -96,7 +96,7 @@ GEOA3_API int geoa3_loss_bwd(const float *adv, const float *ori, const float *nr
  * pointnet2_ops  (replaces the 9 functions exported by _ext-src/src/bindings.cpp:6-19)
  * ---------------------------------------------------------------------------------------------- */
 
-/* xyz [b][n][3] -> idx [b][m]; same selection (origin skip, 1e10 init, (k mod BS,k) tie order) as
+/* xyz [b][n][3] -> idx [b][m]; same selection (origin skip, 1e10 init, tournament tie order) as
  * furthest_point_sampling (sampling.cpp:66-87, sampling_gpu.cu:69-229).  No temp buffer needed. */
 GEOA3_API int geoa3_furthest_point_sampling(const float *xyz, int b, int n, int m, int32_t *idx, geoa3_stream_t stream);
 

@@ -8,6 +8,9 @@
  * -ffp-contract=off); value-producing routines (losses, kappa, gradients) are
  * evaluated in fp64 from the fp32 inputs and compared at 1e-5 relative.
  *
+ * Two distance chains are pinned: the kNN loop of pytorch3d (`dist += diff*diff`, x then y then z) and the
+ * contracted pointnet2_ops expression (y then x then z, see dist2f_pn2).  They differ in the last ulp.
+ *
  * Reference statements followed (paths relative to /root/reference):
  *   Lib/loss_utils.py:28-35   chamfer_loss        -> orc_loss_fwd (cd)
  *   Lib/loss_utils.py:45-50   hausdorff_loss      -> orc_loss_fwd (hd)
@@ -42,6 +45,17 @@ static inline float dist2f(float px, float py, float pz, float qx, float qy, flo
   float dx = px - qx, dy = py - qy, dz = pz - qz;
   float t = dx * dx;
   t = fmaf(dy, dy, t);
+  t = fmaf(dz, dz, t);
+  return t;
+}
+
+/* pointnet2_ops kernels: the source expression (dx*dx)+(dy*dy)+(dz*dz) is contracted by nvcc into
+ * t=dy*dy; t=fma(dx,dx,t); t=fma(dz,dz,t)  (read off the SASS of the reference compiled for sm_100:
+ * FPS, ball_query and three_nn all start from the y term). */
+static inline float dist2f_pn2(float px, float py, float pz, float qx, float qy, float qz) {
+  float dx = px - qx, dy = py - qy, dz = pz - qz;
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
   t = fmaf(dz, dz, t);
   return t;
 }
@@ -244,9 +258,9 @@ ORC_API void orc_fps(const float *xyz, int b, int n, int m, int32_t *idxs) {
         float best = -1.f;
         for (int k = tid; k < n; k += BS) {
           float x2 = p[k * 3], y2 = p[k * 3 + 1], z2 = p[k * 3 + 2];
-          float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+          float mag = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
           if ((double)mag <= 1e-3) continue;
-          float d = dist2f(x2, y2, z2, x1, y1, z1);
+          float d = dist2f_pn2(x2, y2, z2, x1, y1, z1);
           float d2 = fminf(d, temp[k]);
           temp[k] = d2;
           besti = d2 > best ? k : besti;
@@ -280,7 +294,7 @@ ORC_API void orc_ball_query(const float *new_xyz, const float *xyz, int b, int n
       for (int l = 0; l < nsample; ++l) out[j * nsample + l] = 0;
       int cnt = 0;
       for (int k = 0; k < n && cnt < nsample; ++k) {
-        float d2 = dist2f(q[j * 3], q[j * 3 + 1], q[j * 3 + 2], p[k * 3], p[k * 3 + 1], p[k * 3 + 2]);
+        float d2 = dist2f_pn2(q[j * 3], q[j * 3 + 1], q[j * 3 + 2], p[k * 3], p[k * 3 + 1], p[k * 3 + 2]);
         if (d2 < radius2) {
           if (cnt == 0)
             for (int l = 0; l < nsample; ++l) out[j * nsample + l] = k;
@@ -343,7 +357,7 @@ ORC_API void orc_three_nn(const float *unknown, const float *known, int b, int n
       double best1 = 1e40, best2 = 1e40, best3 = 1e40;
       int b1 = 0, b2 = 0, b3 = 0;
       for (int k = 0; k < m; ++k) {
-        float d = dist2f(u[j * 3], u[j * 3 + 1], u[j * 3 + 2], kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]);
+        float d = dist2f_pn2(u[j * 3], u[j * 3 + 1], u[j * 3 + 2], kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]);
         if (d < best1) {
           best3 = best2; b3 = b2; best2 = best1; b2 = b1; best1 = d; b1 = k;
         } else if (d < best2) {

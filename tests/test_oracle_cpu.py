@@ -77,7 +77,7 @@ def test_fps_semantics():
     # hand case: 1-D points, start at 0, farthest-first order is determined
     xyz = np.zeros((1, 6, 3), np.float32)
     xyz[0, :, 0] = [1.0, 2.0, 4.0, 8.0, 3.0, 7.5]
-    assert list(O.fps(xyz, 4)[0]) == [0, 3, 2, 4]  # last pick: d(1)=d(4)=1, (k mod 4, k) => 4
+    assert list(O.fps(xyz, 4)[0]) == [0, 3, 2, 4]  # last pick: d(1)=d(4)=1, thread 0 (k=4) keeps the tie
     # origin skip: a point with |p|^2 <= 1e-3 is never selected (sampling_gpu.cu:100-101)
     xyz2 = xyz.copy()
     xyz2[0, 3] = [0.01, 0.0, 0.0]
@@ -85,8 +85,8 @@ def test_fps_semantics():
     # all candidates skipped -> index 0 (besti = 0)
     z = np.full((1, 8, 3), 1e-3, np.float32)
     assert list(O.fps(z, 5)[0]) == [0, 0, 0, 0, 0]
-    # tie order: equal distances -> smallest (k mod BS, k); n=6 => BS=4, so k=1 (1 mod 4) beats k=4 (0 mod 4)? no:
-    # (k mod BS, k) for k=4 is (0,4) < (1,1) => index 4 wins
+    # tie order: equal distances -> smallest bit-reversed reference thread id (k mod BS), then smallest k;
+    # n=6 => BS=4: k=4 runs on thread 0, k=1 on thread 1 => index 4 wins
     t = np.zeros((1, 6, 3), np.float32)
     t[0, :, 0] = [5.0, 6.0, 5.0, 5.0, 4.0, 5.0]  # from point 0: d(1)=1, d(4)=1
     t[0, :, 1] = 1.0
@@ -129,7 +129,7 @@ def test_three_nn_interpolate():
     u = rng.standard_normal((1, 11, 3)).astype(np.float32)
     kn = rng.standard_normal((1, 23, 3)).astype(np.float32)
     d, i = O.three_nn(u, kn)
-    D = O.pairdist(np.ascontiguousarray(u.transpose(0, 2, 1)), np.ascontiguousarray(kn.transpose(0, 2, 1)))
+    D = ((u[:, :, None, :].astype(np.float64) - kn[:, None, :, :]) ** 2).sum(-1)
     assert np.array_equal(i, np.argsort(D, 2, kind="stable")[:, :, :3].astype(np.int32))
     w = rng.uniform(size=(1, 11, 3)).astype(np.float32)
     pts = rng.standard_normal((1, 4, 23)).astype(np.float32)

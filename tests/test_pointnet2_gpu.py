@@ -71,6 +71,50 @@ def test_ball_query_bitexact(b, n, m, r, ns):
         assert torch.equal(got, ext.ball_query(cu(new), cu(xyz), r, ns))
 
 
+def _shell(rng, n, centre, r):
+    """n points at distance r (+- a few ulp) from `centre`: every ball / arg-max decision is ulp-critical"""
+    u = rng.standard_normal((n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    return (np.asarray(centre, np.float64) + r * u).astype(np.float32)
+
+
+def test_ball_query_ulp_critical_vs_reference_binary():
+    """Points on the ball's surface: membership flips with the last ulp of d2, so this only passes when the
+    distance arithmetic (contraction order y,x,z) matches the reference binary exactly."""
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(5)
+    b, n, m, ns = 4, 2048, 16, 256
+    r = np.float32(0.3)
+    new = rng.uniform(-0.5, 0.5, (b, m, 3)).astype(np.float32)
+    xyz = np.stack([np.concatenate([_shell(rng, n // m, new[i, j], float(r)) for j in range(m)]) for i in range(b)])
+    got = pu.ball_query(float(r), ns, cu(xyz), cu(new))
+    assert np.array_equal(got.cpu().numpy(), O.ball_query(new, xyz, float(r), ns))
+    inside = (got.cpu().numpy() != got.cpu().numpy()[:, :, :1]).sum()
+    assert inside > 1000  # the shell really straddles the boundary (neither all in nor all out)
+    ext = ref_ext()
+    if ext is not None:
+        assert torch.equal(got, ext.ball_query(cu(new), cu(xyz), float(r), ns))
+
+
+def test_fps_ulp_critical_vs_reference_binary():
+    """All points (nearly) equidistant from the start point and from each other's images: arg-max decided by ulps."""
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(6)
+    xs = []
+    for i in range(6):
+        c = rng.uniform(0.3, 0.6, 3)
+        pts = _shell(rng, 1023, c, 0.25)
+        xs.append(np.concatenate([c[None].astype(np.float32), pts]))
+    xyz = np.stack(xs)
+    got = pu.furthest_point_sample(cu(xyz), 256)
+    assert np.array_equal(got.cpu().numpy(), O.fps(xyz, 256))
+    ext = ref_ext()
+    if ext is not None:
+        assert torch.equal(got, ext.furthest_point_sampling(cu(xyz), 256))
+
+
 @pytest.mark.parametrize("b,c,n,m,ns", [(4, 3, 1024, 512, 64), (4, 128, 512, 128, 64), (2, 67, 300, 50, 7),
                                         (2, 320, 512, 128, 128)])
 def test_group_points_and_grad(b, c, n, m, ns):
@@ -137,6 +181,8 @@ def test_three_nn_interpolate():
     if ext is not None:
         rd, ri = ext.three_nn(cu(unknown), cu(known))
         assert torch.equal(ri, idx) and torch.equal(torch.sqrt(rd), dist)
+        assert torch.equal(out.detach(), ext.three_interpolate(cu(pts), idx, cu(w)))  # bit-exact vs the binary
+        assert rel_err(p.grad.cpu().numpy(), ext.three_interpolate_grad(cu(go), idx, cu(w), m).cpu().numpy()) < 1e-5
 
 
 def test_query_and_group_module():

@@ -1,0 +1,40 @@
+"""Launches every kernel of the hot path exactly once at BASELINE config-2/3 sizes — the target of the
+ncu captures committed under profiles/ (see DESIGN.md).  Not a benchmark: never quote its timings."""
+import os.path as osp
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
+from geoa3_b200 import ops  # noqa: E402
+from oracle import synth  # noqa: E402
+
+b, n, k = 250, 1024, 16
+pc, nr, _ = synth.make_batch(10, n)
+ori = torch.from_numpy(np.tile(pc, (25, 1, 1))).cuda()
+nrm = torch.from_numpy(np.tile(nr, (25, 1, 1))).cuda()
+adv = ori + torch.from_numpy(synth.make_offsets(b, n)).cuda()
+d1, js, d2, is_ = ops.nn_pair(adv, ori)
+nbr = ops.knn(adv, adv, k + 1, drop=1)[0]
+ko = ops.kappa_loss_fwd(ori, normal=nrm, nbr=nbr)["kappa"]
+out = ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr, d_a2o=d1, d_o2a=d2, kappa_ori=ko, want_nrm=True,
+                         want_cd=True, want_hd=True, want_curv=True)
+g = torch.full((b,), 1.0 / b, device="cuda")
+ops.loss_bwd(adv, ori=ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=ko, jstar=js, istar=is_, nbr=nbr,
+             hd_arg=out["hd_arg"], g_cd=g, g_hd=g, g_cu=g)
+if "--pn2" in sys.argv:
+    xyz = ori.transpose(1, 2).contiguous()
+    fi = ops.furthest_point_sampling(xyz, 512)
+    new = ops.gather_points(ori, fi).transpose(1, 2).contiguous()
+    idx = ops.ball_query(new, xyz, 0.2, 64)
+    ops.group_points(ori, idx)
+    feats = torch.randn(b, 128, 512, device="cuda")
+    fi2 = ops.furthest_point_sampling(new, 128)
+    new2 = ops.gather_points(new.transpose(1, 2).contiguous(), fi2).transpose(1, 2).contiguous()
+    idx2 = ops.ball_query(new2, new, 0.4, 64)
+    ops.group_points(feats, idx2)
+    ops.group_points_grad(torch.randn(b, 128, 128, 64, device="cuda"), idx2, 512)
+    ops.group_points_grad(torch.randn(b, 3, 512, 64, device="cuda"), idx, 1024)
+torch.cuda.synchronize()
+print("done")

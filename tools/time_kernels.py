@@ -1,0 +1,113 @@
+"""Per-kernel CUDA-event timings of the hot path at BASELINE config sizes (run on the GPU box).
+   python tools/time_kernels.py [--b 250 --n 1024 --k 16]   -> JSON lines on stdout"""
+import argparse
+import json
+import os.path as osp
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
+from geoa3_b200 import ops  # noqa: E402
+from oracle import synth  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=5, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--b", type=int, default=250)
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--pn2", action="store_true")
+    a = ap.parse_args()
+    b, n, k = a.b, a.n, a.k
+    pc, nr, _ = synth.make_batch(min(b, 20), n)
+    reps = (b + pc.shape[0] - 1) // pc.shape[0]
+    ori = torch.from_numpy(np.tile(pc, (reps, 1, 1))[:b].copy()).cuda()
+    nrm = torch.from_numpy(np.tile(nr, (reps, 1, 1))[:b].copy()).cuda()
+    adv = ori + torch.from_numpy(synth.make_offsets(b, n)).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    res["nn_pair"] = timeit(lambda: ops.nn_pair(adv, ori), flush=flush)
+    d1, js, d2, is_ = ops.nn_pair(adv, ori)
+    res["knn_self"] = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1), flush=flush)
+    nbr = ops.knn(adv, adv, k + 1, drop=1)[0]
+    nbr_o = ops.knn(ori, ori, k + 1, drop=1)[0]
+    ko = ops.kappa_loss_fwd(ori, normal=nrm, nbr=nbr_o)["kappa"]
+    f = lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr, d_a2o=d1, d_o2a=d2, kappa_ori=ko, want_nrm=True,
+                                   want_cd=True, want_hd=True, want_curv=True)
+    res["kappa_loss_fwd"] = timeit(f, flush=flush)
+    out = f()
+    g = torch.full((b,), 1.0 / b, device="cuda")
+    res["loss_bwd"] = timeit(lambda: ops.loss_bwd(adv, ori=ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=ko,
+                                                  jstar=js, istar=is_, nbr=nbr, hd_arg=out["hd_arg"], g_cd=g, g_hd=g,
+                                                  g_cu=g), flush=flush)
+    tot = sum(v[0] for v in res.values())
+    pairs = b * n * n
+    print(json.dumps(dict(what="loss_path", b=b, n=n, k=k, us_median={k_: round(v[0], 2) for k_, v in res.items()},
+                          us_min={k_: round(v[1], 2) for k_, v in res.items()}, total_us=round(tot, 2),
+                          nn_pair_Gpairs_s=round(2 * pairs / res["nn_pair"][0] / 1e3, 1),
+                          knn_Gpairs_s=round(pairs / res["knn_self"][0] / 1e3, 1),
+                          hbm_frac=round(52 * b * n / (tot * 1e-6) / 6555.2e9, 4))))
+    if a.pn2:
+        xyz = ori.transpose(1, 2).contiguous()
+        r = {}
+        r["fps_1024_512"] = timeit(lambda: ops.furthest_point_sampling(xyz, 512), iters=5, warm=2)
+        fi = ops.furthest_point_sampling(xyz, 512)
+        new = ops.gather_points(ori, fi).transpose(1, 2).contiguous()
+        r["ball_query_r.2_ns64"] = timeit(lambda: ops.ball_query(new, xyz, 0.2, 64), flush=flush)
+        idx = ops.ball_query(new, xyz, 0.2, 64)
+        r["group_c3"] = timeit(lambda: ops.group_points(ori, idx), flush=flush)
+        feats = torch.randn(b, 128, 512, device="cuda")
+        fi2 = ops.furthest_point_sampling(new, 128)
+        new2 = ops.gather_points(new.transpose(1, 2).contiguous(), fi2).transpose(1, 2).contiguous()
+        r["fps_512_128"] = timeit(lambda: ops.furthest_point_sampling(new, 128), iters=5, warm=2)
+        idx2 = ops.ball_query(new2, new, 0.4, 64)
+        r["ball_query_r.4_ns64_n512"] = timeit(lambda: ops.ball_query(new2, new, 0.4, 64), flush=flush)
+        r["group_c128"] = timeit(lambda: ops.group_points(feats, idx2), flush=flush)
+        go = torch.randn(b, 128, 128, 64, device="cuda")
+        r["group_grad_c128"] = timeit(lambda: ops.group_points_grad(go, idx2, 512), flush=flush)
+        go3 = torch.randn(b, 3, 512, 64, device="cuda")
+        r["group_grad_c3"] = timeit(lambda: ops.group_points_grad(go3, idx, 1024), flush=flush)
+        gb = b * 128 * 128 * 64 * 4 / 1e9
+        print(json.dumps(dict(what="pointnet2", b=b, us_median={k_: round(v[0], 2) for k_, v in r.items()},
+                              group_c128_GBs=round(gb / (r["group_c128"][0] * 1e-6), 1),
+                              group_grad_c128_GBs=round(gb / (r["group_grad_c128"][0] * 1e-6), 1))))
+        ext = None
+        try:
+            from oracle import build_ref
+            ext = build_ref.load_ref()
+        except Exception as e:  # noqa
+            print(json.dumps(dict(ref_ext_error=str(e))))
+        if ext is not None:
+            rr = {}
+            rr["fps_1024_512"] = timeit(lambda: ext.furthest_point_sampling(xyz, 512), iters=5, warm=2)
+            rr["ball_query_r.2_ns64"] = timeit(lambda: ext.ball_query(new, xyz, 0.2, 64), iters=5, warm=2)
+            rr["group_c3"] = timeit(lambda: ext.group_points(ori, idx), iters=5, warm=2)
+            rr["group_c128"] = timeit(lambda: ext.group_points(feats, idx2), iters=5, warm=2)
+            rr["group_grad_c128"] = timeit(lambda: ext.group_points_grad(go, idx2, 512), iters=5, warm=2)
+            rr["fps_512_128"] = timeit(lambda: ext.furthest_point_sampling(new, 128), iters=5, warm=2)
+            print(json.dumps(dict(what="pointnet2_reference_kernels_sm100", b=b,
+                                  us_median={k_: round(v[0], 2) for k_, v in rr.items()})))
+
+
+if __name__ == "__main__":
+    main()
