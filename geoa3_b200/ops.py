@@ -7,6 +7,14 @@ from . import _lib
 from ._lib import check, ptr, require_cuda_f32, require_cuda_i32, stream
 
 
+LAUNCHES = 0  # own kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _guard(t):
     return torch.cuda.device(t.device)
 
@@ -23,6 +31,7 @@ def nn_pair(adv, ori, both=True):
     d2 = torch.empty(b, m, device=adv.device, dtype=torch.float32) if both else None
     i2 = torch.empty(b, m, device=adv.device, dtype=torch.int32) if both else None
     with _guard(adv):
+        _count(1)
         check(_lib.load().geoa3_nn_pair(ptr(adv), ptr(ori), b, n, m, ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(adv)))
     return d1, j1, d2, i2
 
@@ -35,6 +44,7 @@ def knn(query, ref, K, drop=0, return_dist=False):
     idx = torch.empty(b, n, K - drop, device=query.device, dtype=torch.int32)
     dist = torch.empty(b, n, K - drop, device=query.device, dtype=torch.float32) if return_dist else None
     with _guard(query):
+        _count(1)
         check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(idx), ptr(dist), stream(query)))
     return idx, dist
 
@@ -56,6 +66,7 @@ def kappa_loss_fwd(pc, normal=None, jstar=None, nbr=None, d_a2o=None, d_o2a=None
     ha = torch.empty(b, device=dev, dtype=torch.int32) if want_hd else None
     cu = torch.empty(b, device=dev, dtype=torch.float32) if (want_curv and k > 0) else None
     with _guard(pc):
+        _count(1)
         check(_lib.load().geoa3_kappa_loss_fwd(ptr(pc), ptr(normal), ptr(jstar), ptr(nbr), k, ptr(d_a2o), ptr(d_o2a),
                                                ptr(kappa_ori), b, n, m, ptr(kap), ptr(nrm), ptr(cd), ptr(hd), ptr(ha),
                                                ptr(cu), stream(pc)))
@@ -76,6 +87,7 @@ def loss_bwd(adv, ori=None, nrm_adv=None, kappa_adv=None, kappa_ori=None, jstar=
         if g is not None:
             require_cuda_f32(g, "upstream gradient")
     with _guard(adv):
+        _count(1)
         check(_lib.load().geoa3_loss_bwd(ptr(adv), ptr(ori), ptr(nrm_adv), ptr(kappa_adv), ptr(kappa_ori), ptr(jstar),
                                          ptr(istar), ptr(nbr), ptr(hd_arg), ptr(g_cd), ptr(g_hd), ptr(g_cu),
                                          ptr(g_kappa), b, n, m, k, ptr(grad), stream(adv)))
@@ -88,6 +100,7 @@ def furthest_point_sampling(points, nsamples):
     b, n, _ = points.shape
     out = torch.empty(b, nsamples, device=points.device, dtype=torch.int32)
     with _guard(points):
+        _count(1)
         check(_lib.load().geoa3_furthest_point_sampling(ptr(points), b, n, nsamples, ptr(out), stream(points)))
     return out
 
@@ -98,6 +111,7 @@ def gather_points(points, idx):
     m = idx.shape[1]
     out = torch.empty(b, c, m, device=points.device, dtype=torch.float32)
     with _guard(points):
+        _count(1)
         check(_lib.load().geoa3_gather_points(ptr(points), ptr(idx), b, c, n, m, ptr(out), stream(points)))
     return out
 
@@ -113,6 +127,7 @@ def gather_points_grad(grad_out, idx, n):
     out = torch.empty(b, c, n, device=grad_out.device, dtype=torch.float32)
     ws, nbytes = _workspace(grad_out.device, b, n, m, 1)
     with _guard(grad_out):
+        _count(2)
         check(_lib.load().geoa3_gather_points_grad(ptr(grad_out), ptr(idx), b, c, n, m, ptr(out), ptr(ws), nbytes,
                                                    stream(grad_out)))
     return out
@@ -124,6 +139,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     m = new_xyz.shape[1]
     idx = torch.empty(b, m, nsample, device=xyz.device, dtype=torch.int32)
     with _guard(xyz):
+        _count(1)
         check(_lib.load().geoa3_ball_query(ptr(new_xyz), ptr(xyz), b, n, m, float(radius), int(nsample), ptr(idx),
                                            stream(xyz)))
     return idx
@@ -135,6 +151,7 @@ def group_points(points, idx):
     _, npoints, nsample = idx.shape
     out = torch.empty(b, c, npoints, nsample, device=points.device, dtype=torch.float32)
     with _guard(points):
+        _count(1)
         check(_lib.load().geoa3_group_points(ptr(points), ptr(idx), b, c, n, npoints, nsample, ptr(out), stream(points)))
     return out
 
@@ -145,6 +162,7 @@ def group_points_grad(grad_out, idx, n):
     out = torch.empty(b, c, n, device=grad_out.device, dtype=torch.float32)
     ws, nbytes = _workspace(grad_out.device, b, n, npoints, nsample)
     with _guard(grad_out):
+        _count(2)
         check(_lib.load().geoa3_group_points_grad(ptr(grad_out), ptr(idx), b, c, n, npoints, nsample, ptr(out), ptr(ws),
                                                   nbytes, stream(grad_out)))
     return out
@@ -157,6 +175,7 @@ def three_nn(unknowns, knows):
     dist2 = torch.empty(b, n, 3, device=unknowns.device, dtype=torch.float32)
     idx = torch.empty(b, n, 3, device=unknowns.device, dtype=torch.int32)
     with _guard(unknowns):
+        _count(1)
         check(_lib.load().geoa3_three_nn(ptr(unknowns), ptr(knows), b, n, m, ptr(dist2), ptr(idx), stream(unknowns)))
     return dist2, idx
 
@@ -167,6 +186,7 @@ def three_interpolate(points, idx, weight):
     n = idx.shape[1]
     out = torch.empty(b, c, n, device=points.device, dtype=torch.float32)
     with _guard(points):
+        _count(1)
         check(_lib.load().geoa3_three_interpolate(ptr(points), ptr(idx), ptr(weight), b, c, m, n, ptr(out),
                                                   stream(points)))
     return out
@@ -178,6 +198,7 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     out = torch.empty(b, c, m, device=grad_out.device, dtype=torch.float32)
     ws, nbytes = _workspace(grad_out.device, b, m, n, 3)
     with _guard(grad_out):
+        _count(2)
         check(_lib.load().geoa3_three_interpolate_grad(ptr(grad_out), ptr(idx), ptr(weight), b, c, n, m, ptr(out),
                                                        ptr(ws), nbytes, stream(grad_out)))
     return out

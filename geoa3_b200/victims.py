@@ -1,0 +1,140 @@
+"""Victim classifiers used by the attack benchmarks.  They stay PyTorch/cuDNN (north star); only the
+PointNet++ sampling/grouping goes through libgeoa3_b200.so.  Architectures follow the reference so its
+checkpoints load by name: PointNet = /root/reference/Model/PointNet.py:56-160 (two T-nets, conv5 is a
+k=3 Conv1d :110), PointNet++ SSG/MSG = Model/PointNetPP_ssg.py:51-124 / Model/PointNetPP_msg.py:9-46."""
+import torch
+import torch.nn as nn
+
+from .pointnet2_ops.pointnet2_modules import PointnetSAModule, PointnetSAModuleMSG
+
+
+def _xavier(*layers):
+    for m in layers:
+        nn.init.xavier_uniform_(m.weight.data)
+        if m.bias is not None:
+            m.bias.data.zero_()
+
+
+class transform_net(nn.Module):
+    """T-net regressing a KxK alignment matrix (PointNet.py:56-95)."""
+
+    def __init__(self, K=3):
+        super().__init__()
+        self.K, self.eps = K, 1e-3
+        self.conv1, self.conv2, self.conv3 = nn.Conv1d(K, 64, 1), nn.Conv1d(64, 128, 1), nn.Conv1d(128, 1024, 1)
+        self.fc1, self.fc2, self.fc3 = nn.Linear(1024, 512), nn.Linear(512, 256), nn.Linear(256, K * K)
+        self.bn1, self.bn2, self.bn3 = (nn.BatchNorm1d(c, eps=self.eps) for c in (64, 128, 1024))
+        self.bn4, self.bn5 = nn.BatchNorm1d(512, eps=self.eps), nn.BatchNorm1d(256, eps=self.eps)
+        self.relu = nn.ReLU(True)
+        _xavier(self.conv1, self.conv2, self.conv3, self.fc1, self.fc2)
+        for bn in (self.bn1, self.bn2, self.bn3, self.bn4, self.bn5):
+            bn.weight.data.fill_(1)
+            bn.bias.data.zero_()
+        self.fc3.weight.data.fill_(0)
+        self.fc3.bias.data.copy_(torch.eye(K).view(-1))
+
+    def forward(self, x):
+        x = self.relu(self.bn1(self.conv1(x)))
+        x = self.relu(self.bn2(self.conv2(x)))
+        x = self.relu(self.bn3(self.conv3(x)))
+        x = x.max(-1)[0]
+        x = self.relu(self.bn4(self.fc1(x)))
+        x = self.relu(self.bn5(self.fc2(x)))
+        return self.fc3(x).view(-1, self.K, self.K)
+
+
+class PointNet(nn.Module):
+    """PointNet classifier on [b,3,n] clouds -> logits [b,classes] (eval) (PointNet.py:97-160)."""
+
+    def __init__(self, classes, return_idx=False, npoint=1024):
+        super().__init__()
+        self.num_class, self.eps, self.return_idx = classes, 1e-3, return_idx
+        self.input_transform, self.feature_transform = transform_net(K=3), transform_net(K=64)
+        self.conv1, self.conv2, self.conv3 = nn.Conv1d(3, 64, 1), nn.Conv1d(64, 64, 1), nn.Conv1d(64, 64, 1)
+        self.conv4, self.conv5 = nn.Conv1d(64, 128, 1), nn.Conv1d(128, 1024, 3, 1, 1)
+        self.bn1, self.bn2, self.bn3 = (nn.BatchNorm1d(64, eps=self.eps) for _ in range(3))
+        self.bn4, self.bn5 = nn.BatchNorm1d(128, eps=self.eps), nn.BatchNorm1d(1024, eps=self.eps)
+        self.fc1, self.bn6 = nn.Linear(1024, 512), nn.BatchNorm1d(512)
+        self.fc2, self.bn7 = nn.Linear(512, 256), nn.BatchNorm1d(256)
+        self.fc3 = nn.Linear(256, classes)
+        self.relu, self.drop1, self.drop2 = nn.ReLU(True), nn.Dropout(p=0.3), nn.Dropout(p=0.3)
+        _xavier(self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.fc1, self.fc2, self.fc3)
+        for bn in (self.bn1, self.bn2, self.bn3, self.bn4, self.bn5, self.bn6, self.bn7):
+            bn.weight.data.fill_(1)
+            bn.bias.data.zero_()
+
+    def forward(self, pc):
+        assert pc.size(1) == 3
+        t = self.input_transform(pc)
+        x = torch.bmm(pc.permute(0, 2, 1), t).permute(0, 2, 1)
+        x = self.relu(self.bn1(self.conv1(x)))
+        x = self.relu(self.bn2(self.conv2(x)))
+        t = self.feature_transform(x)
+        x = torch.bmm(x.permute(0, 2, 1), t).permute(0, 2, 1)
+        x = self.relu(self.bn3(self.conv3(x)))
+        x = self.relu(self.bn4(self.conv4(x)))
+        x = self.relu(self.bn5(self.conv5(x)))
+        x, idx = x.max(-1)
+        x = self.drop1(self.relu(self.bn6(self.fc1(x))))
+        x = self.drop2(self.relu(self.bn7(self.fc2(x))))
+        out = self.fc3(x)
+        if self.training:
+            return out, t
+        return (out, idx) if self.return_idx else out
+
+
+class PointNet2ClassificationSSG(nn.Module):
+    """PointNet++ single-scale-grouping classifier, input [b,3(+C),n] (PointNetPP_ssg.py:51-124)."""
+
+    def __init__(self, use_xyz=True, use_normal=False):
+        super().__init__()
+        self.use_xyz, self.use_normal = use_xyz, use_normal
+        self._build_model()
+
+    def _build_model(self):
+        c0 = 3 if self.use_normal else 0
+        self.SA_modules = nn.ModuleList([
+            PointnetSAModule(npoint=512, radius=0.2, nsample=64, mlp=[c0, 64, 64, 128], use_xyz=self.use_xyz),
+            PointnetSAModule(npoint=128, radius=0.4, nsample=64, mlp=[128, 128, 128, 256], use_xyz=self.use_xyz),
+            PointnetSAModule(mlp=[256, 256, 512, 1024], use_xyz=self.use_xyz),
+        ])
+        self.fc_layer = nn.Sequential(
+            nn.Linear(1024, 512, bias=False), nn.BatchNorm1d(512), nn.ReLU(True),
+            nn.Linear(512, 256, bias=False), nn.BatchNorm1d(256), nn.ReLU(True),
+            nn.Dropout(0.5), nn.Linear(256, 40))
+
+    def forward(self, pointcloud):
+        pointcloud = pointcloud.transpose(2, 1)
+        xyz = pointcloud[..., 0:3].contiguous()
+        features = pointcloud[..., 3:].transpose(1, 2).contiguous() if pointcloud.size(-1) > 3 else None
+        for sa in self.SA_modules:
+            xyz, features = sa(xyz, features)
+        return self.fc_layer(features.squeeze(-1))
+
+
+class PointNet2ClassificationMSG(PointNet2ClassificationSSG):
+    """Multi-scale-grouping variant (PointNetPP_msg.py:9-46)."""
+
+    def _build_model(self):
+        super()._build_model()
+        c0 = 3 if self.use_normal else 0
+        c1 = 64 + 128 + 128
+        self.SA_modules = nn.ModuleList([
+            PointnetSAModuleMSG(npoint=512, radii=[0.1, 0.2, 0.4], nsamples=[16, 32, 128],
+                                mlps=[[c0, 32, 32, 64], [c0, 64, 64, 128], [c0, 64, 96, 128]], use_xyz=self.use_xyz),
+            PointnetSAModuleMSG(npoint=128, radii=[0.2, 0.4, 0.8], nsamples=[32, 64, 128],
+                                mlps=[[c1, 64, 64, 128], [c1, 128, 128, 256], [c1, 128, 128, 256]],
+                                use_xyz=self.use_xyz),
+            PointnetSAModule(mlp=[128 + 256 + 256, 256, 512, 1024], use_xyz=self.use_xyz),
+        ])
+
+
+def build_victim(arch, classes=40):
+    """`--arch` names of main_attack.py:134-147."""
+    if arch == "PointNet":
+        return PointNet(classes, npoint=1024)
+    if arch == "PointNetPP_ssg":
+        return PointNet2ClassificationSSG(use_xyz=True, use_normal=False)
+    if arch == "PointNetPP_msg":
+        return PointNet2ClassificationMSG(use_xyz=True, use_normal=False)
+    raise ValueError("unknown arch " + str(arch))

@@ -1,0 +1,85 @@
+"""GPU tests of the attack driver (the caller of the hot path): graph replay == eager, sharded == unsharded,
+reference return convention."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(b, n, start=0):
+    pc, nr, lab = synth.make_batch(b, n, start)
+    return [torch.from_numpy(pc).permute(0, 2, 1)[:, None].contiguous(), torch.from_numpy(nr).permute(0, 2, 1)[:, None].contiguous(),
+            torch.from_numpy(lab)[:, None]]
+
+
+def _net():
+    from geoa3_b200.victims import build_victim
+
+    torch.manual_seed(0)
+    return build_victim("PointNet").cuda().eval()
+
+
+def test_attack_return_convention_and_graph_equals_eager():
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=2, iter_max_steps=6, curv_loss_knn=8)
+    data = _data(3, 256)
+    out_g = atk.attack(net, data, cfg, use_cuda_graph=True)
+    out_e = atk.attack(net, data, cfg, use_cuda_graph=False)
+    best, target, success, steps, losses = out_g
+    assert best.shape == (3, 3, 256) and target.shape == (3,) and success.dtype == np.bool_ and len(steps) == 3
+    assert len(losses) == 6 and len(losses[0]) == 3
+    assert np.allclose(np.asarray(losses), np.asarray(out_e[4]), rtol=1e-4, atol=1e-5)
+    assert list(success) == list(out_e[2])
+
+
+def test_sharded_equals_unsharded():
+    from geoa3_b200 import attack as atk
+    from geoa3_b200 import dist as gd
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=5, curv_loss_knn=8)
+    data = _data(4, 256)
+    full = atk.attack(net, data, cfg, use_cuda_graph=False)
+    parts = []
+    for r in range(2):
+        rows = gd.shard_rows(4, 2, r)
+        sl = [d[rows.start:rows.stop] for d in data]
+        parts.append(atk.attack(net, sl, cfg, use_cuda_graph=False, global_batch=4, rows=list(rows)))
+    cat = np.concatenate([np.asarray(p[4]) for p in parts], 1)
+    assert np.allclose(cat, np.asarray(full[4]), rtol=1e-4, atol=1e-5)
+
+
+def test_projection_helpers():
+    from geoa3_b200 import attack as atk
+    from oracle import oracle as O
+
+    pc, nr, _ = synth.make_batch(2, 200, 2)
+    off = synth.make_offsets(2, 200, std=5e-2)
+    P, N_, F_ = torch.from_numpy(pc).cuda(), torch.from_numpy(nr).cuda(), torch.from_numpy(off).cuda()
+    real = atk.find_offset(P, P + F_)
+    _, j = O.nn1(pc + off, pc)
+    exp = (pc + off) - np.take_along_axis(pc, j[:, None, :].repeat(3, 1), 2)
+    assert np.allclose(real.cpu().numpy(), exp, atol=1e-7)
+    proj = atk.offset_proj(F_, P, N_)
+    _, j2 = O.nn1(off, pc)  # the reference queries with the raw offset (geoA3_attack.py:65)
+    nn_ = np.take_along_axis(nr, j2[:, None, :].repeat(3, 1), 2)
+    u = nn_ / (np.sqrt((nn_ ** 2).sum(1, keepdims=True)) + 1e-6)
+    assert np.allclose(proj.cpu().numpy(), (off * u).sum(1, keepdims=True) * u, atol=1e-6)
+    clip = atk.lp_clip(F_, 0.01)
+    assert float((clip ** 2).sum(1).sqrt().max()) <= 0.01 * (1 + 1e-5)
+
+
+def test_pointnetpp_attack_step_runs():
+    from geoa3_b200 import attack as atk
+    from geoa3_b200.victims import build_victim
+
+    torch.manual_seed(0)
+    net = build_victim("PointNetPP_ssg").cuda().eval()
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=3)
+    out = atk.attack(net, _data(2, 1024), cfg, use_cuda_graph=True)
+    assert np.isfinite(np.asarray(out[4])).all()
