@@ -81,7 +81,7 @@ def lp_clip(offset, cc_linf):
 
 # ------------------------------------------------------------------ loss assembly
 def forward_step(net, pc_ori, input_curr_iter, normal_ori, ori_kappa, target, scale_const, cfg, targeted,
-                 loss_divisor=None):
+                 loss_divisor=None, hints=None):
     """Mirror of `_forward_step` (:100-180) without the four `.item()` syncs.  Returns
     (logits, loss, loss_n, cls_loss, dis_loss, hd_loss, curv_loss, constrain_loss)."""
     b = input_curr_iter.size(0)
@@ -109,7 +109,7 @@ def forward_step(net, pc_ori, input_curr_iter, normal_ori, ori_kappa, target, sc
         assert w_hd == 0
     if w_cd != 0 or w_hd != 0 or w_cu != 0:
         geo, cd, hd, cu = loss_utils.geo_loss(input_curr_iter, pc_ori, normal_ori, ori_kappa, _get(cfg, "curv_loss_knn"),
-                                              w_cd, w_hd, w_cu, single_side=_get(cfg, "is_cd_single_side"))
+                                              w_cd, w_hd, w_cu, single_side=_get(cfg, "is_cd_single_side"), hints=hints)
     else:
         geo, cd, hd, cu = zero, zero, zero, zero
     constrain = geo
@@ -160,6 +160,7 @@ class AttackState(object):
             raise AssertionError("Not support such optimizer.")
         self.gamma = 0.9990
         self.graph = None
+        self.hints = loss_utils.HintBuffers()  # previous step's argmin / kNN indices seed the next search
 
     def reset_global(self):
         """Back to the state of a fresh attack() call (used after the CUDA-graph warm-up/capture)."""
@@ -196,7 +197,7 @@ class AttackState(object):
         input_all = self.pc_ori + self.offset
         logits, loss, loss_n, cls_loss, dis, hd, cu, constrain = forward_step(
             self.net, self.pc_ori, input_all, self.normal_ori, self.kappa_ori, self.target, self.scale_const, cfg,
-            self.targeted, loss_divisor=self.global_batch)
+            self.targeted, loss_divisor=self.global_batch, hints=self.hints)
         with torch.no_grad():
             pred = logits.argmax(1)
             success = _compare(pred, self.target, self.gt_target, self.targeted)

@@ -89,9 +89,10 @@ kappa_loss_fwd_kernel(const float* __restrict__ pc, const float* __restrict__ no
       for (int t = 0; t < k; ++t) {
         const float4 pj = pts[nbi[t]];
         const float vx = pj.x - pi.x, vy = pj.y - pi.y, vz = pj.z - pi.z;
-        const float L = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), KL_EPS);
-        const float ux = __fdiv_rn(vx, L), uy = __fdiv_rn(vy, L), uz = __fdiv_rn(vz, L);
-        acc += fabsf(ux * nx + uy * ny + uz * nz);
+        // v / max(|v|, 1e-12): |v| >= 1e-12 <=> |v|^2 >= 1e-24; MUFU.RSQ is accurate to ~1e-7 relative
+        const float s2 = vx * vx + vy * vy + vz * vz;
+        const float inv = s2 >= 1e-24f ? rsqrtf(s2) : 1e12f;
+        acc += fabsf((vx * nx + vy * ny + vz * nz) * inv);
       }
       kap = acc * inv_k;
       if (kappa) kappa[gi] = kap;
@@ -127,10 +128,10 @@ kappa_loss_fwd_kernel(const float* __restrict__ pc, const float* __restrict__ no
 
 // d|<n, v/|v|>| / dv scaled by f0 = gk/k  (clamp at 1e-12 passes no grad to the norm)
 __device__ __forceinline__ float3 dkappa_dv(float vx, float vy, float vz, float nx, float ny, float nz, float f0) {
-  const float L = sqrtf(vx * vx + vy * vy + vz * vz);
+  const float s2 = vx * vx + vy * vy + vz * vz;
   float3 r;
-  if (L >= KL_EPS) {
-    const float inv = 1.f / L;
+  if (s2 >= 1e-24f) {  // |v| >= 1e-12
+    const float inv = rsqrtf(s2);
     const float ux = vx * inv, uy = vy * inv, uz = vz * inv;
     const float s = ux * nx + uy * ny + uz * nz;
     const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
@@ -162,7 +163,7 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
   float4* nrm = reinterpret_cast<float4*>(smem_raw + lay.nrm);
   int* offs1 = reinterpret_cast<int*>(smem_raw + lay.offs1);
   int* offs2 = reinterpret_cast<int*>(smem_raw + lay.offs2);
-  int* whist = reinterpret_cast<int*>(smem_raw + lay.whist);
+  uint16_t* whist = reinterpret_cast<uint16_t*>(smem_raw + lay.whist);
   uint16_t* ent1 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent1);
   uint16_t* ent2 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent2);
   __shared__ int scan_scratch[KL_WARPS + 1];
@@ -188,8 +189,8 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
     pts[i] = make_float4(a[i], a[n + i], a[2 * n + i], gk);
   }
   __syncthreads();
-  if (do_curv) build_csr<KL_THREADS>(nbr + (size_t)cloud * n * k, n * k, n, k, offs1, whist, lay.W, ent1, scan_scratch);
-  if (do_col) build_csr<KL_THREADS>(istar + (size_t)cloud * m, m, n, 1, offs2, whist, lay.W, ent2, scan_scratch);
+  if (do_curv) build_csr<KL_THREADS, uint16_t, uint16_t>(nbr + (size_t)cloud * n * k, n * k, n, k, offs1, whist, lay.W, ent1, scan_scratch);
+  if (do_col) build_csr<KL_THREADS, uint16_t, uint16_t>(istar + (size_t)cloud * m, m, n, 1, offs2, whist, lay.W, ent2, scan_scratch);
 
   const int ha = (g_hd && hd_arg) ? hd_arg[cloud] : -1;
   const float w_row = gcd * (2.f / (float)n), w_col = gcd * (2.f / (float)m);
@@ -247,7 +248,7 @@ static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdL
     L->nrm = take(do_curv ? (size_t)16 * n : 0);
     L->offs1 = take(do_curv ? (size_t)4 * (n + 1) : 0);
     L->offs2 = take(do_col ? (size_t)4 * (n + 1) : 0);
-    L->whist = take((do_curv || do_col) ? (size_t)4 * W * n : 0);
+    L->whist = take((do_curv || do_col) ? (size_t)2 * W * n : 0);
     L->ent1 = take(do_curv ? (size_t)2 * n * k : 0);
     L->ent2 = take(do_col ? (size_t)2 * m : 0);
     L->total = off;
@@ -298,7 +299,7 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
   if (do_curv) GEOA3_CHECK_ARG(nrm_adv);
   if (g_cu && do_curv) GEOA3_CHECK_ARG(kappa_adv && kappa_ori && jstar);
   const bool do_col = istar && g_cd;
-  if (n > 65535 || m > 65535) return GEOA3_EUNSUPPORTED;  // CSR entries are uint16
+  if (n > 65535 || m > 65535 || (size_t)n * (size_t)(k > 0 ? k : 1) > 65535) return GEOA3_EUNSUPPORTED;  // uint16 CSR
   BwdLayout L;
   if (!plan_bwd_layout(n, m, k, do_curv, do_col, &L)) return GEOA3_EUNSUPPORTED;
   static bool attr_done = false;

@@ -9,6 +9,14 @@
 // lane every step): they are appended to a small per-thread queue in shared memory and the warp
 // drains all queues together — a branch-free sorted-insert network executed by all 32 lanes — when
 // any lane's queue is nearly full.  The queue preserves arrival order, so ties keep their order.
+//
+// Hinted threshold.  Scanning in index order from tau = +inf inserts ~K*ln(N/K) candidates per query, and the
+// insert network (5 alu ops per list slot) is what the half-width alu pipe chokes on.  If the caller passes,
+// per query, a list of candidate indices (typically the neighbours found one optimisation step earlier),
+// tau starts at the largest exact distance to those candidates — an upper bound of the true K-th distance
+// whenever the list (plus the query's own index) holds K distinct points — so only ~K candidates are ever
+// inserted.  The bound is self-verifying: if fewer than K candidates passed it the CTA rescans with
+// tau = +inf.  Any hint therefore yields the exact lexicographic top-K; a bad one only costs time.
 #include "common.cuh"
 
 namespace geoa3 {
@@ -46,7 +54,7 @@ struct TopK {
 template <int K>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n, int m, int kout, int drop,
-           int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+           const int32_t* hint, int hint_k, int32_t* idx_out, float* __restrict__ dist_out) {
   __shared__ __align__(16) float sx[KNN_CHUNK];
   __shared__ __align__(16) float sy[KNN_CHUNK];
   __shared__ __align__(16) float sz[KNN_CHUNK];
@@ -62,9 +70,25 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   const float qx = qbase[qq], qy = qbase[n + qq], qz = qbase[2 * n + qq];
   const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
 
+  // hinted start threshold: max exact distance to the hinted candidates and to the point of the same index
+  // (the self match of a self-query), nudged one ulp up so that the strict test below admits equality.
+  float tau0 = __int_as_float(0x7f800000);
+  if (hint != nullptr && hint_k + 1 >= K) {
+    const int32_t* h = hint + ((size_t)cloud * n + qq) * hint_k;  // may alias idx_out: own row, read before write
+    const int s0 = min(qq, m - 1);
+    float mx = dist2(cbase[s0], cbase[m + s0], cbase[2 * m + s0], qx, qy, qz);
+    for (int t = 0; t < hint_k; ++t) {
+      const int j = min(max(h[t], 0), m - 1);
+      mx = fmaxf(mx, dist2(cbase[j], cbase[m + j], cbase[2 * m + j], qx, qy, qz));
+    }
+    if (mx < 3.0e38f) tau0 = __uint_as_float(__float_as_uint(mx) + 1u);
+  }
+
   TopK<K> top;
+  bool rescan = false;
+  do {
   top.init();
-  float tau = top.tau();
+  float tau = tau0;
   int cnt = 0;
 
   auto drain = [&]() {
@@ -76,7 +100,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
       top.insert(x, xi);
     }
     cnt = 0;
-    tau = top.tau();
+    tau = fminf(tau0, top.tau());
   };
 
   for (int c0 = 0; c0 < m; c0 += KNN_CHUNK) {
@@ -105,6 +129,10 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
     }
   }
   drain();
+  // fewer than K candidates under the hinted bound => the bound was not valid for this query: redo unhinted
+  rescan = __syncthreads_or((qi < n) && top.i[K - 1] < 0 && tau0 != __int_as_float(0x7f800000));
+  tau0 = __int_as_float(0x7f800000);
+  } while (rescan);
 
   if (qi < n) {
     int32_t* io = idx_out + ((size_t)cloud * n + qi) * kout;
@@ -122,28 +150,28 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
 
 template <int K>
 static int launch_knn(const float* query, const float* ref, int b, int n, int m, int kout, int drop,
-                      int32_t* idx, float* dist, cudaStream_t s) {
+                      const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
   dim3 grid(ceil_div(n, KNN_THREADS), b, 1);
-  knn_kernel<K><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, idx, dist);
+  knn_kernel<K><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, hint, hint_k, idx, dist);
   return GEOA3_LAUNCH_RESULT();
 }
 
 }  // namespace geoa3
 
 extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int m, int K, int drop,
-                         int32_t* idx, float* dist, geoa3_stream_t stream) {
+                         const int32_t* hint, int hint_k, int32_t* idx, float* dist, geoa3_stream_t stream) {
   using namespace geoa3;
   GEOA3_CHECK_ARG(query && ref && idx);
-  GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K);
+  GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
   if (K > GEOA3_KNN_MAX_K || b > 65535) return GEOA3_EUNSUPPORTED;
   if (K > m) return GEOA3_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const int kout = K - drop;
   // the list size is a compile-time constant (register arrays); a larger list than requested is still
   // exact: the first K entries of the top-K' (K' >= K) are the top-K.
-  if (K <= 3) return launch_knn<3>(query, ref, b, n, m, kout, drop, idx, dist, s);
-  if (K <= 5) return launch_knn<5>(query, ref, b, n, m, kout, drop, idx, dist, s);
-  if (K <= 9) return launch_knn<9>(query, ref, b, n, m, kout, drop, idx, dist, s);
-  if (K <= 17) return launch_knn<17>(query, ref, b, n, m, kout, drop, idx, dist, s);
-  return launch_knn<33>(query, ref, b, n, m, kout, drop, idx, dist, s);
+  if (K <= 3) return launch_knn<3>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
+  if (K <= 5) return launch_knn<5>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
+  if (K <= 9) return launch_knn<9>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
+  if (K <= 17) return launch_knn<17>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
+  return launch_knn<33>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
 }

@@ -1,11 +1,18 @@
 // nn_pair.cu — fused bidirectional 1-NN (Chamfer / Hausdorff / normal borrowing front end).
 //
-// One launch covers both directions (blockIdx.z): each CTA owns a tile of queries of one cloud and
-// streams the cloud's candidates through shared memory (SoA x[],y[],z[] so that one LDS.128 feeds
-// four candidates to every lane as a broadcast).  Each thread keeps Q queries in registers and
-// evaluates two candidates per instruction with the packed fp32 pipe (FADD2/FMUL2/FFMA2).  The
-// N x M matrix only ever exists as registers; per query the running (min, argmin) is updated with
-// strict '<' while candidates are visited in ascending index => ties resolve to the lowest index.
+// One launch covers both directions: each CTA owns a tile of queries of one cloud and streams the
+// cloud's candidates through shared memory (SoA x[],y[],z[]: one LDS.128 feeds four candidates to every
+// lane as a broadcast).  Each thread keeps Q queries in registers and evaluates two candidates per
+// instruction on the packed fp32 pipe (FADD2/FMUL2/FFMA2).  The N x M matrix only ever exists as registers.
+//
+// Seeded exact search.  On B200 the alu pipe (FSETP/FSEL/SEL/FMNMX, 16 lanes/clk/SMSP) is half as wide
+// as the fma pipe, so a per-pair compare+select+index update (3 alu ops) costs as much as the distance
+// itself.  Instead every query starts from a seed candidate (caller hint, default: the point with the
+// same index — in the attack adv_i is a perturbed ori_i) whose exact distance initialises `best`; the
+// hot loop then only folds 8 distances into one FMNMX tree and asks "min <= best?" (1 alu op per pair).
+// Only when that fires does the thread walk the 8 candidates with the exact lexicographic rule
+// (d < best) or (d == best and j < argbest), so the result is the same (min, lowest index) the plain
+// ascending scan produces — for ANY seed; a bad seed only costs speed.
 #include "common.cuh"
 
 namespace geoa3 {
@@ -13,12 +20,13 @@ namespace geoa3 {
 constexpr int NN_THREADS = 256;
 constexpr int NN_Q = 2;          // queries per thread
 constexpr int NN_CHUNK = 2048;   // candidates staged per shared-memory pass (24 KB)
+constexpr float NN_INF = __builtin_huge_valf();
 
 template <int Q>
 __global__ void __launch_bounds__(NN_THREADS)
 nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int n, int m,
-               float* __restrict__ d_a2o, int32_t* __restrict__ jstar,
-               float* __restrict__ d_o2a, int32_t* __restrict__ istar, int tiles_a) {
+               const int32_t* hint_a2o, const int32_t* hint_o2a,
+               float* __restrict__ d_a2o, int32_t* jstar, float* __restrict__ d_o2a, int32_t* istar, int tiles_a) {
   __shared__ __align__(16) float sx[NN_CHUNK];
   __shared__ __align__(16) float sy[NN_CHUNK];
   __shared__ __align__(16) float sz[NN_CHUNK];
@@ -34,6 +42,8 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
   const int nc = dir1 ? n : m;
   float* dout = dir1 ? d_o2a + (size_t)cloud * m : d_a2o + (size_t)cloud * n;
   int32_t* iout = dir1 ? istar + (size_t)cloud * m : jstar + (size_t)cloud * n;
+  const int32_t* hint = dir1 ? hint_o2a : hint_a2o;  // may alias iout: each thread reads its own slot first
+  if (hint) hint += (size_t)cloud * nq;
 
   float2 nqx[Q], nqy[Q], nqz[Q];
   float best[Q];
@@ -43,42 +53,46 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
   for (int q = 0; q < Q; ++q) {
     qi[q] = tile * (NN_THREADS * Q) + q * NN_THREADS + threadIdx.x;
     const int qq = min(qi[q], nq - 1);
-    const float x = -qbase[qq], y = -qbase[nq + qq], z = -qbase[2 * nq + qq];
-    nqx[q] = make_float2(x, x);
-    nqy[q] = make_float2(y, y);
-    nqz[q] = make_float2(z, z);
-    best[q] = __int_as_float(0x7f800000);
-    bi[q] = 0;
+    const float x = qbase[qq], y = qbase[nq + qq], z = qbase[2 * nq + qq];
+    nqx[q] = make_float2(-x, -x);
+    nqy[q] = make_float2(-y, -y);
+    nqz[q] = make_float2(-z, -z);
+    int seed = hint ? hint[qq] : qq;
+    seed = min(max(seed, 0), nc - 1);
+    best[q] = dist2(cbase[seed], cbase[nc + seed], cbase[2 * nc + seed], x, y, z);  // == packed result, bit for bit
+    bi[q] = seed;
   }
 
   for (int c0 = 0; c0 < nc; c0 += NN_CHUNK) {
     const int cn = min(NN_CHUNK, nc - c0);
-    const int cn4 = (cn + 3) & ~3;
+    const int cn8 = (cn + 7) & ~7;
     __syncthreads();
-    for (int t = threadIdx.x; t < cn4; t += NN_THREADS) {
+    for (int t = threadIdx.x; t < cn8; t += NN_THREADS) {
       const bool ok = t < cn;
-      // padding candidates sit at +inf: their distance is +inf and can never win a strict '<'
-      sx[t] = ok ? cbase[c0 + t] : __int_as_float(0x7f800000);
+      // padding candidates sit at +inf: their distance is +inf, never <= a finite best
+      sx[t] = ok ? cbase[c0 + t] : NN_INF;
       sy[t] = ok ? cbase[nc + c0 + t] : 0.f;
       sz[t] = ok ? cbase[2 * nc + c0 + t] : 0.f;
     }
     __syncthreads();
-#pragma unroll 2
-    for (int j = 0; j < cn4; j += 4) {
-      const float4 cx = *reinterpret_cast<const float4*>(sx + j);
-      const float4 cy = *reinterpret_cast<const float4*>(sy + j);
-      const float4 cz = *reinterpret_cast<const float4*>(sz + j);
+    for (int j = 0; j < cn8; j += 8) {
+      const float4 cxa = *reinterpret_cast<const float4*>(sx + j), cxb = *reinterpret_cast<const float4*>(sx + j + 4);
+      const float4 cya = *reinterpret_cast<const float4*>(sy + j), cyb = *reinterpret_cast<const float4*>(sy + j + 4);
+      const float4 cza = *reinterpret_cast<const float4*>(sz + j), czb = *reinterpret_cast<const float4*>(sz + j + 4);
       const int jj = c0 + j;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const float2 d01 = dist2x2(make_float2(cx.x, cx.y), make_float2(cy.x, cy.y), make_float2(cz.x, cz.y),
-                                   nqx[q], nqy[q], nqz[q]);
-        const float2 d23 = dist2x2(make_float2(cx.z, cx.w), make_float2(cy.z, cy.w), make_float2(cz.z, cz.w),
-                                   nqx[q], nqy[q], nqz[q]);
-        if (d01.x < best[q]) { best[q] = d01.x; bi[q] = jj; }
-        if (d01.y < best[q]) { best[q] = d01.y; bi[q] = jj + 1; }
-        if (d23.x < best[q]) { best[q] = d23.x; bi[q] = jj + 2; }
-        if (d23.y < best[q]) { best[q] = d23.y; bi[q] = jj + 3; }
+        const float2 d01 = dist2x2(make_float2(cxa.x, cxa.y), make_float2(cya.x, cya.y), make_float2(cza.x, cza.y), nqx[q], nqy[q], nqz[q]);
+        const float2 d23 = dist2x2(make_float2(cxa.z, cxa.w), make_float2(cya.z, cya.w), make_float2(cza.z, cza.w), nqx[q], nqy[q], nqz[q]);
+        const float2 d45 = dist2x2(make_float2(cxb.x, cxb.y), make_float2(cyb.x, cyb.y), make_float2(czb.x, czb.y), nqx[q], nqy[q], nqz[q]);
+        const float2 d67 = dist2x2(make_float2(cxb.z, cxb.w), make_float2(cyb.z, cyb.w), make_float2(czb.z, czb.w), nqx[q], nqy[q], nqz[q]);
+        const float mn = fminf(fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)), fminf(fminf(d45.x, d45.y), fminf(d67.x, d67.y)));
+        if (mn <= best[q]) {  // rare: exact lexicographic update over the 8 candidates
+          const float dd[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (dd[t] < best[q] || (dd[t] == best[q] && jj + t < bi[q])) { best[q] = dd[t]; bi[q] = jj + t; }
+        }
       }
     }
   }
@@ -92,8 +106,9 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
 
 }  // namespace geoa3
 
-extern "C" int geoa3_nn_pair(const float* adv, const float* ori, int b, int n, int m, float* d_a2o,
-                             int32_t* jstar, float* d_o2a, int32_t* istar, geoa3_stream_t stream) {
+extern "C" int geoa3_nn_pair(const float* adv, const float* ori, int b, int n, int m, const int32_t* hint_a2o,
+                             const int32_t* hint_o2a, float* d_a2o, int32_t* jstar, float* d_o2a, int32_t* istar,
+                             geoa3_stream_t stream) {
   using namespace geoa3;
   GEOA3_CHECK_ARG(adv && ori && d_a2o && jstar);
   GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0);
@@ -103,7 +118,7 @@ extern "C" int geoa3_nn_pair(const float* adv, const float* ori, int b, int n, i
   const int tiles_a = ceil_div(n, per);
   const int tiles_b = d_o2a ? ceil_div(m, per) : 0;
   dim3 grid(tiles_a + tiles_b, b, 1);
-  nn_pair_kernel<NN_Q><<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(adv, ori, n, m, d_a2o, jstar, d_o2a, istar,
-                                                                      tiles_a);
+  nn_pair_kernel<NN_Q><<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(adv, ori, n, m, hint_a2o, hint_o2a, d_a2o, jstar,
+                                                                      d_o2a, istar, tiles_a);
   return GEOA3_LAUNCH_RESULT();
 }

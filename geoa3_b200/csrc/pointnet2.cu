@@ -66,27 +66,28 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits
   int old = 0;
   for (int j = 1; j < m; ++j) {
     const float x1 = s_xyz[old], y1 = s_xyz[n + old], z1 = s_xyz[2 * n + old];
-    unsigned bh = 0u, bl = 0u;  // best (hi, lo); (0,0) = no candidate
+    // branch-free update: frozen / out-of-range points carry tk == 0 and contribute the minimal key (0,0)
+    float hmax = 0.f;
 #pragma unroll
     for (int t = 0; t < P; ++t) {
-      if (tk[t] != 0u) {
-        const float d = dist2_pn2(px[t], py[t], pz[t], x1, y1, z1);
-        temp[t] = fminf(d, temp[t]);
-        const unsigned h = __float_as_uint(temp[t]);
-        if (h > bh || (h == bh && tk[t] > bl)) { bh = h; bl = tk[t]; }
-      }
+      const float d = dist2_pn2(px[t], py[t], pz[t], x1, y1, z1);
+      temp[t] = fminf(d, temp[t]);
+      hmax = fmaxf(hmax, tk[t] != 0u ? temp[t] : 0.f);  // distances are >= +0: float order == bit order
     }
-    // warp arg-max of the 64-bit key in two REDUX steps
+    unsigned bl = 0u;
+#pragma unroll
+    for (int t = 0; t < P; ++t) bl = max(bl, temp[t] == hmax ? tk[t] : 0u);
+    const unsigned bh = __float_as_uint(hmax);
+    // warp arg-max of the 64-bit key (bh, bl) in two REDUX steps
     const unsigned mh = __reduce_max_sync(0xffffffffu, bh);
     const unsigned ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
     if (lane == 0) s_part[j & 1][w] = ((unsigned long long)mh << 32) | ml;
     __syncthreads();
-    unsigned long long best = 0ull;
-    for (int i = 0; i < nw; ++i) {
-      const unsigned long long v = s_part[j & 1][i];
-      best = v > best ? v : best;
-    }
-    const unsigned lo = (unsigned)best;
+    // cross-warp arg-max, lane-parallel (nw <= 32 partials), again two REDUX steps; every warp redundantly
+    const unsigned long long pv = lane < nw ? s_part[j & 1][lane] : 0ull;
+    const unsigned ph = (unsigned)(pv >> 32), pl = (unsigned)pv;
+    const unsigned gh = __reduce_max_sync(0xffffffffu, ph);
+    const unsigned lo = __reduce_max_sync(0xffffffffu, ph == gh ? pl : 0u);
     old = lo != 0u ? (int)((~lo) & 0xFFFFFu) : 0;
     if (tid == 0) out[j] = old;
   }
@@ -189,7 +190,7 @@ csr_global_kernel(const int32_t* __restrict__ idx, int E, int n, int W, int* __r
   const int cloud = blockIdx.x;
   int* offs = ws + (size_t)cloud * (n + 1 + E);
   int* ent = offs + n + 1;
-  build_csr<CSRG_THREADS>(idx + (size_t)cloud * E, E, n, 1, offs, s_whist, W, ent, scan_scratch);
+  build_csr<CSRG_THREADS, int, int>(idx + (size_t)cloud * E, E, n, 1, offs, s_whist, W, ent, scan_scratch);
 }
 
 // grad_points[b][c][p] = sum over segment(p) of grad_out[b][c][e] (ascending e), optional weights

@@ -19,33 +19,49 @@ def _guard(t):
     return torch.cuda.device(t.device)
 
 
-def nn_pair(adv, ori, both=True):
-    """adv [b,3,n], ori [b,3,m] -> d_a2o [b,n], jstar [b,n] i32, d_o2a [b,m] | None, istar [b,m] | None"""
+def nn_pair(adv, ori, both=True, hint_a2o=None, hint_o2a=None, out=None):
+    """adv [b,3,n], ori [b,3,m] -> d_a2o [b,n], jstar [b,n] i32, d_o2a [b,m] | None, istar [b,m] | None.
+    hint_* (int32, optional) seed the search (exact for any seed); `out` = (d1, j1, d2, i2) preallocated
+    buffers (j1/i2 may be the hint tensors themselves: in-place refresh of persistent hints)."""
     require_cuda_f32(adv, "adv_pc"); require_cuda_f32(ori, "ori_pc")
     b, c, n = adv.shape
     m = ori.shape[2]
     if c != 3 or ori.shape[0] != b or ori.shape[1] != 3:
         raise RuntimeError("expected [b,3,n] and [b,3,m] clouds")
-    d1 = torch.empty(b, n, device=adv.device, dtype=torch.float32)
-    j1 = torch.empty(b, n, device=adv.device, dtype=torch.int32)
-    d2 = torch.empty(b, m, device=adv.device, dtype=torch.float32) if both else None
-    i2 = torch.empty(b, m, device=adv.device, dtype=torch.int32) if both else None
+    if out is not None:
+        d1, j1, d2, i2 = out
+    else:
+        d1 = torch.empty(b, n, device=adv.device, dtype=torch.float32)
+        j1 = torch.empty(b, n, device=adv.device, dtype=torch.int32)
+        d2 = torch.empty(b, m, device=adv.device, dtype=torch.float32) if both else None
+        i2 = torch.empty(b, m, device=adv.device, dtype=torch.int32) if both else None
+    for h in (hint_a2o, hint_o2a):
+        if h is not None:
+            require_cuda_i32(h, "hint")
     with _guard(adv):
         _count(1)
-        check(_lib.load().geoa3_nn_pair(ptr(adv), ptr(ori), b, n, m, ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(adv)))
+        check(_lib.load().geoa3_nn_pair(ptr(adv), ptr(ori), b, n, m, ptr(hint_a2o), ptr(hint_o2a) if both else None,
+                                        ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(adv)))
     return d1, j1, d2, i2
 
 
-def knn(query, ref, K, drop=0, return_dist=False):
-    """query [b,3,n], ref [b,3,m] -> idx [b,n,K-drop] i32 (ascending (dist,idx)), dist | None"""
+def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None):
+    """query [b,3,n], ref [b,3,m] -> idx [b,n,K-drop] i32 (ascending (dist,idx)), dist | None.
+    hint [b,n,hk] int32 (optional) only tightens the start threshold (exact for any hint); `out` may be the
+    hint tensor itself (in-place refresh)."""
     require_cuda_f32(query, "query"); require_cuda_f32(ref, "ref")
     b, _, n = query.shape
     m = ref.shape[2]
-    idx = torch.empty(b, n, K - drop, device=query.device, dtype=torch.int32)
+    idx = out if out is not None else torch.empty(b, n, K - drop, device=query.device, dtype=torch.int32)
+    hk = 0
+    if hint is not None:
+        require_cuda_i32(hint, "hint")
+        hk = hint.shape[2]
     dist = torch.empty(b, n, K - drop, device=query.device, dtype=torch.float32) if return_dist else None
     with _guard(query):
         _count(1)
-        check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(idx), ptr(dist), stream(query)))
+        check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(hint), hk, ptr(idx), ptr(dist),
+                                    stream(query)))
     return idx, dist
 
 

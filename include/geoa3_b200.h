@@ -55,17 +55,23 @@ GEOA3_API const char *geoa3_error_string(int code);
  * tiled through shared memory and never written.  d_a2o[b][n]/jstar[b][n] = min_j / argmin_j
  * d(adv_i, ori_j); d_o2a[b][m]/istar[b][m] the other direction (pass NULL for both to skip it:
  * pseudo_chamfer_loss, hausdorff_loss, find_offset).
+ * hint_a2o [b][n] / hint_o2a [b][m] (nullable) seed each query with a candidate index (default: its own
+ * index); results are exact for any seed, a good one (e.g. last step's argmin) makes the search ~2x faster.
+ * A hint may alias the corresponding output (in-place update of a persistent buffer).
  * Replaces: knn_points(adv, ori, K=1) + knn_points(ori, adv, K=1), Lib/loss_utils.py:32-33,41,48,70,92;
  *           Attacker/geoA3_attack.py:65,80. */
-GEOA3_API int geoa3_nn_pair(const float *adv, const float *ori, int b, int n, int m, float *d_a2o, int32_t *jstar,
-                  float *d_o2a, int32_t *istar, geoa3_stream_t stream);
+GEOA3_API int geoa3_nn_pair(const float *adv, const float *ori, int b, int n, int m, const int32_t *hint_a2o,
+                            const int32_t *hint_o2a, float *d_a2o, int32_t *jstar, float *d_o2a, int32_t *istar,
+                            geoa3_stream_t stream);
 
 /* K nearest of every query [b][3][n] among ref [b][3][m], ascending (dist, idx); the first `drop`
  * columns are discarded (drop=1 removes the self match exactly like "[:,:,:,1:]").
  * idx [b][n][K-drop] int32, dist (nullable) [b][n][K-drop].  K <= GEOA3_KNN_MAX_K, K <= m.
+ * hint [b][n][hint_k] (nullable): candidate indices per query used only to start the selection threshold
+ * (self-verifying, results are exact for any hint); may alias idx when hint_k == K-drop.
  * Replaces: knn_points(pc, pc, K=k+1).idx[..., 1:], Lib/loss_utils.py:57-58,77-78,139,174. */
-GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int m, int K, int drop, int32_t *idx,
-              float *dist, geoa3_stream_t stream);
+GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int m, int K, int drop,
+                        const int32_t *hint, int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
 
 /* Local curvature + per-cloud loss reductions, one CTA per cloud, fixed-order reductions.
  *   kappa_i = (1/k) sum_m |<nrm_i, v_im/max(|v_im|,1e-12)>|,  v_im = pc[nbr[i][m]] - pc[i]

@@ -200,3 +200,66 @@ def test_full_size_properties():
     z = Oc.clone().requires_grad_(True)
     (L.chamfer_loss(z, Oc) + L.hausdorff_loss(z, Oc)).sum().backward()
     assert float(z.grad.abs().max()) == 0.0
+
+
+def test_hints_never_change_results():
+    """Seeds / hinted thresholds are accelerators only: good, stale, adversarial and garbage hints all give
+    the oracle's indices (including the in-place aliased form the attack driver uses)."""
+    from geoa3_b200 import ops
+
+    adv, ori, _ = make(3, 1000, 4, 5e-2)
+    A, Oc = cu(adv), cu(ori)
+    od1, oj1 = O.nn1(adv, ori)
+    od2, oi2 = O.nn1(ori, adv)
+    oi, od = O.knn(adv, adv, 17)
+    rng = np.random.default_rng(0)
+    garbage = torch.from_numpy(rng.integers(-5, 2000, (3, 1000)).astype(np.int32)).cuda()
+    good_j, good_i = cu(oj1), cu(oi2)
+    worst = torch.from_numpy(np.argmax(O.pairdist(adv, ori), 2).astype(np.int32)).cuda()
+    for hj, hi in ((good_j, good_i), (garbage, garbage), (worst, worst), (None, garbage)):
+        d1, j1, d2, i2 = ops.nn_pair(A, Oc, hint_a2o=hj, hint_o2a=hi)
+        assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
+        assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    # in place: buffers are hint and output at once
+    bj, bi_ = garbage.clone(), worst.clone()
+    bd1, bd2 = torch.empty(3, 1000, device="cuda"), torch.empty(3, 1000, device="cuda")
+    ops.nn_pair(A, Oc, hint_a2o=bj, hint_o2a=bi_, out=(bd1, bj, bd2, bi_))
+    assert np.array_equal(bj.cpu().numpy(), oj1) and np.array_equal(bi_.cpu().numpy(), oi2)
+    # kNN: exact hint, hint from a different (shifted) cloud, duplicated / garbage hint rows, far-away hint
+    exact = cu(oi[:, :, 1:])
+    other = cu(O.knn(ori, ori, 17)[0][:, :, 1:])
+    dup = torch.zeros(3, 1000, 16, dtype=torch.int32, device="cuda")
+    junk = torch.from_numpy(rng.integers(-3, 1500, (3, 1000, 16)).astype(np.int32)).cuda()
+    far = torch.from_numpy(np.argsort(-O.pairdist(adv, adv), 2)[:, :, :16].astype(np.int32)).cuda()
+    for h in (exact, other, dup, junk, far):
+        idx, dist = ops.knn(A, A, 17, drop=0, return_dist=True, hint=h)
+        assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    buf = other.clone()
+    ops.knn(A, A, 17, drop=1, hint=buf, out=buf)
+    assert np.array_equal(buf.cpu().numpy(), oi[:, :, 1:])
+    # lattice ties with hints
+    pc, _ = synth.lattice_cloud(343)
+    pc = np.stack([pc, pc * 0.5])
+    oi2_, _ = O.knn(pc, pc, 9)
+    h = cu(oi2_[:, :, 1:][:, :, ::-1].copy())
+    idx, _ = ops.knn(cu(pc), cu(pc), 9, hint=h)
+    assert np.array_equal(idx.cpu().numpy(), oi2_)
+
+
+def test_attack_state_hints_match_unhinted():
+    from geoa3_b200 import loss_utils as L
+
+    adv, ori, nrm = make(4, 1024, 7, 1e-2)
+    ko = L._get_kappa_ori(cu(ori), cu(nrm), 16)
+    hb = L.HintBuffers()
+    outs = []
+    for step in range(3):
+        a_np = adv + synth.make_offsets(4, 1024, seed=10 + step, std=2e-3)
+        res = []
+        for hints in (hb, None):
+            L.clear_cache()
+            a = cu(a_np).requires_grad_(True)
+            tot, cd, hd, cv = L.geo_loss(a, cu(ori), cu(nrm), ko, 16, 1.0, 0.1, 1.0, hints=hints)
+            tot.sum().backward()
+            res.append((tot.detach().clone(), a.grad.clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -17,6 +17,10 @@ nrm = torch.from_numpy(np.tile(nr, (25, 1, 1))).cuda()
 adv = ori + torch.from_numpy(synth.make_offsets(b, n)).cuda()
 d1, js, d2, is_ = ops.nn_pair(adv, ori)
 nbr = ops.knn(adv, adv, k + 1, drop=1)[0]
+adv_prev = adv - 0.003 * torch.sign(torch.randn_like(adv))
+nbr_prev = ops.knn(adv_prev, adv_prev, k + 1, drop=1)[0]
+ops.nn_pair(adv, ori, hint_a2o=js, hint_o2a=is_)      # seeded with last step's argmins (2nd nn_pair launch)
+ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev)       # hinted threshold (3rd knn launch)
 ko = ops.kappa_loss_fwd(ori, normal=nrm, nbr=nbr)["kappa"]
 out = ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr, d_a2o=d1, d_o2a=d2, kappa_ori=ko, want_nrm=True,
                          want_cd=True, want_hd=True, want_curv=True)

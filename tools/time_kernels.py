@@ -48,8 +48,14 @@ def main():
     res = {}
     res["nn_pair"] = timeit(lambda: ops.nn_pair(adv, ori), flush=flush)
     d1, js, d2, is_ = ops.nn_pair(adv, ori)
+    res["nn_pair_hinted"] = timeit(lambda: ops.nn_pair(adv, ori, hint_a2o=js, hint_o2a=is_), flush=flush)
     res["knn_self"] = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1), flush=flush)
     nbr = ops.knn(adv, adv, k + 1, drop=1)[0]
+    # hint = neighbours of the previous attack step (adv moved by one Adam step ~ lr*sign = 0.01 per coordinate at most)
+    adv_prev = adv - 0.003 * torch.sign(torch.randn_like(adv))
+    nbr_prev = ops.knn(adv_prev, adv_prev, k + 1, drop=1)[0]
+    res["knn_self_hinted"] = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev), flush=flush)
+    assert torch.equal(ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev)[0], nbr)
     nbr_o = ops.knn(ori, ori, k + 1, drop=1)[0]
     ko = ops.kappa_loss_fwd(ori, normal=nrm, nbr=nbr_o)["kappa"]
     f = lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr, d_a2o=d1, d_o2a=d2, kappa_ori=ko, want_nrm=True,
@@ -60,7 +66,7 @@ def main():
     res["loss_bwd"] = timeit(lambda: ops.loss_bwd(adv, ori=ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=ko,
                                                   jstar=js, istar=is_, nbr=nbr, hd_arg=out["hd_arg"], g_cd=g, g_hd=g,
                                                   g_cu=g), flush=flush)
-    tot = sum(v[0] for v in res.values())
+    tot = res["nn_pair_hinted"][0] + res["knn_self_hinted"][0] + res["kappa_loss_fwd"][0] + res["loss_bwd"][0]
     pairs = b * n * n
     print(json.dumps(dict(what="loss_path", b=b, n=n, k=k, us_median={k_: round(v[0], 2) for k_, v in res.items()},
                           us_min={k_: round(v[1], 2) for k_, v in res.items()}, total_us=round(tot, 2),

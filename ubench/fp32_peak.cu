@@ -22,12 +22,31 @@ __global__ void __launch_bounds__(256) k(float* out, int iters) {
     } else if (MODE == 1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], m2, c2);
-    } else {
+    } else if (MODE == 2) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         p[i] = __ffma2_rn(p[i], m2, c2);
         mn = fminf(mn, p[i].x);
         mn = fminf(mn, p[i].y);
+      }
+    } else if (MODE == 3) {  // the distance mix: 3 FADD2 + FMUL2 + 2 FFMA2 per 2 pairs (12 "fma-equivalents")
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const float2 dx = __fadd2_rn(p[i], c2), dy = __fadd2_rn(p[i + 1], m2), dz = __fadd2_rn(p[i], m2);
+        float2 t = __fmul2_rn(dx, dx);
+        t = __ffma2_rn(dy, dy, t);
+        t = __ffma2_rn(dz, dz, t);
+        p[i] = t;
+      }
+    } else {  // distance mix + one FMNMX per pair (the seeded nn_pair hot loop)
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const float2 dx = __fadd2_rn(p[i], c2), dy = __fadd2_rn(p[i + 1], m2), dz = __fadd2_rn(p[i], m2);
+        float2 t = __fmul2_rn(dx, dx);
+        t = __ffma2_rn(dy, dy, t);
+        t = __ffma2_rn(dz, dz, t);
+        p[i] = t;
+        mn = fminf(mn, fminf(t.x, t.y));
       }
     }
   }
@@ -65,6 +84,8 @@ int main() {
     run<0>("ffma_scalar", d, 1 << 16);
     run<1>("ffma2_packed", d, 1 << 16);
     run<2>("ffma2_plus_2fmnmx_per_pair", d, 1 << 16);
+    run<3>("dist_mix_4x(3fadd2+fmul2+2ffma2)_per_iter[tflops_field=x16/24_of_real]", d, 1 << 16);
+    run<4>("dist_mix_plus_fmnmx[same]", d, 1 << 16);
   }
   return 0;
 }
