@@ -4,16 +4,18 @@
 //   forward : kappa_i, borrowed normals, CD / HD(+argmax) / curvature-loss reductions in fixed order;
 //   backward: d(g_cd*CD + g_hd*HD + g_cu*CUR + <g_kappa,kappa>)/d adv.  Scatter terms (Chamfer column
 //             term through istar, curvature neighbour term through nbr) are turned into gathers: a
-//             CSR-by-target list is built in shared memory with a warp-ordered counting sort
-//             (match.any ranks inside a warp, per-warp histograms across warps), so every target sums
+//             CSR-by-target list is built in shared memory (integer shared atomics hand out the slots,
+//             then every target sorts its short segment by source id — csr.cuh), so every target sums
 //             its contributions in ascending source order — no float atomics, bitwise reproducible.
 #include "common.cuh"
 #include "csr.cuh"
 
 namespace geoa3 {
 
-constexpr int KL_THREADS = 512;
+constexpr int KL_THREADS = 512;   // forward: one CTA per cloud
 constexpr int KL_WARPS = KL_THREADS / 32;
+constexpr int BW_THREADS = 1024;  // backward: one CTA per cloud, one target per thread at n = 1024
+constexpr int BW_WARPS = BW_THREADS / 32;
 constexpr float KL_EPS = 1e-12f;  // utility.py:30 _normalize eps
 
 // ---------------------------------------------------------------- block helpers (fixed order)
@@ -146,11 +148,13 @@ __device__ __forceinline__ float3 dkappa_dv(float vx, float vy, float vz, float 
   return r;
 }
 
+__device__ long long g_dbg[8];
 struct BwdLayout {  // byte offsets into dynamic shared memory
   int pts, nrm, offs1, offs2, whist, ent1, ent2, total, W;
+  unsigned k_magic;  // ceil(2^32 / k)
 };
 
-__global__ void __launch_bounds__(KL_THREADS)
+__global__ void __launch_bounds__(BW_THREADS, 2)
 loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, const float* __restrict__ nrm_adv,
                 const float* __restrict__ kappa_adv, const float* __restrict__ kappa_ori,
                 const int32_t* __restrict__ jstar, const int32_t* __restrict__ istar,
@@ -163,10 +167,10 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
   float4* nrm = reinterpret_cast<float4*>(smem_raw + lay.nrm);
   int* offs1 = reinterpret_cast<int*>(smem_raw + lay.offs1);
   int* offs2 = reinterpret_cast<int*>(smem_raw + lay.offs2);
-  uint16_t* whist = reinterpret_cast<uint16_t*>(smem_raw + lay.whist);
+  int* whist = reinterpret_cast<int*>(smem_raw + lay.whist);  // n counters / fill cursors
   uint16_t* ent1 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent1);
   uint16_t* ent2 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent2);
-  __shared__ int scan_scratch[KL_WARPS + 1];
+  __shared__ int scan_scratch[BW_WARPS + 1];
 
   const int cloud = blockIdx.x, tid = threadIdx.x;
   const float* a = adv + (size_t)cloud * 3 * n;
@@ -177,7 +181,8 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
   const float ghd = g_hd ? g_hd[cloud] : 0.f;
   const float gcu = g_cu ? g_cu[cloud] : 0.f;
 
-  for (int i = tid; i < n; i += KL_THREADS) {
+  long long T0 = clock64();
+  for (int i = tid; i < n; i += BW_THREADS) {
     const size_t gi = (size_t)cloud * n + i;
     float gk = 0.f;
     if (do_curv) {
@@ -189,13 +194,19 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
     pts[i] = make_float4(a[i], a[n + i], a[2 * n + i], gk);
   }
   __syncthreads();
-  if (do_curv) build_csr<KL_THREADS, uint16_t, uint16_t>(nbr + (size_t)cloud * n * k, n * k, n, k, offs1, whist, lay.W, ent1, scan_scratch);
-  if (do_col) build_csr<KL_THREADS, uint16_t, uint16_t>(istar + (size_t)cloud * m, m, n, 1, offs2, whist, lay.W, ent2, scan_scratch);
+  long long T1 = clock64();
+  if (do_curv)
+    build_csr_sorted<BW_THREADS, uint16_t>(nbr + (size_t)cloud * n * k, n * k, n, lay.k_magic, offs1, whist, ent1,
+                                           scan_scratch, g_dbg);
+  long long T2 = clock64();
+  if (do_col)
+    build_csr_sorted<BW_THREADS, uint16_t>(istar + (size_t)cloud * m, m, n, 0u, offs2, whist, ent2, scan_scratch);
+  long long T3 = clock64();
 
   const int ha = (g_hd && hd_arg) ? hd_arg[cloud] : -1;
   const float w_row = gcd * (2.f / (float)n), w_col = gcd * (2.f / (float)m);
   const float inv_k = k > 0 ? 1.f / (float)k : 0.f;
-  for (int p = tid; p < n; p += KL_THREADS) {
+  for (int p = tid; p < n; p += BW_THREADS) {
     const size_t gp = (size_t)cloud * n + p;
     const float4 ap = pts[p];
     float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -218,10 +229,23 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
       const float f0 = ap.w * inv_k;
       const int32_t* nbp = nbr + gp * k;
       float ox = 0.f, oy = 0.f, oz = 0.f;
-      for (int t = 0; t < k; ++t) {
-        const float4 aj = pts[nbp[t]];
-        const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
-        ox += dv.x; oy += dv.y; oz += dv.z;
+      if ((k & 3) == 0) {  // 16-byte rows: fetch four neighbour indices per load
+        for (int t = 0; t < k; t += 4) {
+          const int4 j4 = *reinterpret_cast<const int4*>(nbp + t);
+          const int js4[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 aj = pts[js4[u]];
+            const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
+            ox += dv.x; oy += dv.y; oz += dv.z;
+          }
+        }
+      } else {
+        for (int t = 0; t < k; ++t) {
+          const float4 aj = pts[nbp[t]];
+          const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
+          ox += dv.x; oy += dv.y; oz += dv.z;
+        }
       }
       gx -= ox; gy -= oy; gz -= oz;
       // incoming terms: every i that lists p as a neighbour, ascending i
@@ -237,18 +261,22 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
     float* g = grad_adv + (size_t)cloud * 3 * n;
     g[p] = gx; g[n + p] = gy; g[2 * n + p] = gz;
   }
+  __syncthreads();
+  long long T4 = clock64();
+  if (cloud == 0 && tid == 0) { g_dbg[0] = T1 - T0; g_dbg[1] = T2 - T1; g_dbg[2] = T3 - T2; g_dbg[3] = T4 - T3; }
 }
 
 static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdLayout* L) {
   const int budget = 227 * 1024 - 256;
-  for (int W = KL_WARPS; W >= 1; W >>= 1) {
+  L->k_magic = k > 1 ? (unsigned)(((1ull << 32) + (unsigned)k - 1) / (unsigned)k) : 0u;
+  for (int W = 16; W >= 1; W >>= 1) {
     int off = 0;
     auto take = [&](size_t bytes) { int o = off; off += (int)((bytes + 15) & ~(size_t)15); return o; };
     L->pts = take((size_t)16 * n);
     L->nrm = take(do_curv ? (size_t)16 * n : 0);
     L->offs1 = take(do_curv ? (size_t)4 * (n + 1) : 0);
     L->offs2 = take(do_col ? (size_t)4 * (n + 1) : 0);
-    L->whist = take((do_curv || do_col) ? (size_t)2 * W * n : 0);
+    L->whist = take(do_curv ? (size_t)2 * W * ((n + 1) & ~1) : (do_col ? (size_t)4 * n : 0));
     L->ent1 = take(do_curv ? (size_t)2 * n * k : 0);
     L->ent2 = take(do_col ? (size_t)2 * m : 0);
     L->total = off;
@@ -260,6 +288,8 @@ static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdL
 }
 
 }  // namespace geoa3
+
+extern "C" __attribute__((visibility("default"))) void geoa3_debug_read(long long* out) { cudaMemcpyFromSymbol(out, geoa3::g_dbg, 64); }
 
 extern "C" int geoa3_kappa_loss_fwd(const float* pc, const float* normal, const int32_t* jstar,
                                     const int32_t* nbr, int k, const float* d_a2o, const float* d_o2a,
@@ -297,6 +327,7 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
   if (g_hd) GEOA3_CHECK_ARG(hd_arg);
   const bool do_curv = k > 0 && nbr && (g_cu || g_kappa);
   if (do_curv) GEOA3_CHECK_ARG(nrm_adv);
+  if (do_curv && k > 32) return GEOA3_EUNSUPPORTED;
   if (g_cu && do_curv) GEOA3_CHECK_ARG(kappa_adv && kappa_ori && jstar);
   const bool do_col = istar && g_cd;
   if (n > 65535 || m > 65535 || (size_t)n * (size_t)(k > 0 ? k : 1) > 65535) return GEOA3_EUNSUPPORTED;  // uint16 CSR
@@ -309,7 +340,7 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  loss_bwd_kernel<<<b, KL_THREADS, L.total, (cudaStream_t)stream>>>(adv, ori, nrm_adv, kappa_adv, kappa_ori, jstar,
+  loss_bwd_kernel<<<b, BW_THREADS, L.total, (cudaStream_t)stream>>>(adv, ori, nrm_adv, kappa_adv, kappa_ori, jstar,
                                                                     istar, nbr, hd_arg, g_cd, g_hd, g_cu, g_kappa, n,
                                                                     m, k, grad_adv, L);
   return GEOA3_LAUNCH_RESULT();

@@ -190,7 +190,7 @@ csr_global_kernel(const int32_t* __restrict__ idx, int E, int n, int W, int* __r
   const int cloud = blockIdx.x;
   int* offs = ws + (size_t)cloud * (n + 1 + E);
   int* ent = offs + n + 1;
-  build_csr<CSRG_THREADS, int, int>(idx + (size_t)cloud * E, E, n, 1, offs, s_whist, W, ent, scan_scratch);
+  build_csr<CSRG_THREADS, int, int>(idx + (size_t)cloud * E, E, n, 0u, offs, s_whist, W, ent, scan_scratch);
 }
 
 // grad_points[b][c][p] = sum over segment(p) of grad_out[b][c][e] (ascending e), optional weights
@@ -328,7 +328,7 @@ static size_t csr_ws_bytes(int b, int n, int E) { return (size_t)b * ((size_t)n 
 
 static int pick_W(int n, int threads) {
   int W = threads / 32;
-  while (W > 1 && (size_t)W * n * 4 > 96 * 1024) W >>= 1;
+  while (W > 1 && (size_t)W * (n + 1) * 4 > 96 * 1024) W >>= 1;
   return W;
 }
 
@@ -336,7 +336,7 @@ static int run_csr_grad(const float* grad_out, const float* weight, const int32_
                         int e_div, float* grad_points, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   if (workspace_bytes < csr_ws_bytes(b, n, E) || !workspace) return GEOA3_EWORKSPACE;
   const int W = pick_W(n, CSRG_THREADS);
-  const size_t sm1 = (size_t)W * n * 4;
+  const size_t sm1 = (size_t)W * ((n + 1) & ~1) * 4;
   if (sm1 > 200 * 1024) return GEOA3_EUNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) {
