@@ -148,7 +148,6 @@ __device__ __forceinline__ float3 dkappa_dv(float vx, float vy, float vz, float 
   return r;
 }
 
-__device__ long long g_dbg[8];
 struct BwdLayout {  // byte offsets into dynamic shared memory
   int pts, nrm, offs1, offs2, whist, ent1, ent2, total, W;
   unsigned k_magic;  // ceil(2^32 / k)
@@ -181,7 +180,6 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
   const float ghd = g_hd ? g_hd[cloud] : 0.f;
   const float gcu = g_cu ? g_cu[cloud] : 0.f;
 
-  long long T0 = clock64();
   for (int i = tid; i < n; i += BW_THREADS) {
     const size_t gi = (size_t)cloud * n + i;
     float gk = 0.f;
@@ -194,14 +192,11 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
     pts[i] = make_float4(a[i], a[n + i], a[2 * n + i], gk);
   }
   __syncthreads();
-  long long T1 = clock64();
   if (do_curv)
     build_csr_sorted<BW_THREADS, uint16_t>(nbr + (size_t)cloud * n * k, n * k, n, lay.k_magic, offs1, whist, ent1,
-                                           scan_scratch, g_dbg);
-  long long T2 = clock64();
+                                           scan_scratch);
   if (do_col)
     build_csr_sorted<BW_THREADS, uint16_t>(istar + (size_t)cloud * m, m, n, 0u, offs2, whist, ent2, scan_scratch);
-  long long T3 = clock64();
 
   const int ha = (g_hd && hd_arg) ? hd_arg[cloud] : -1;
   const float w_row = gcd * (2.f / (float)n), w_col = gcd * (2.f / (float)m);
@@ -261,9 +256,6 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
     float* g = grad_adv + (size_t)cloud * 3 * n;
     g[p] = gx; g[n + p] = gy; g[2 * n + p] = gz;
   }
-  __syncthreads();
-  long long T4 = clock64();
-  if (cloud == 0 && tid == 0) { g_dbg[0] = T1 - T0; g_dbg[1] = T2 - T1; g_dbg[2] = T3 - T2; g_dbg[3] = T4 - T3; }
 }
 
 static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdLayout* L) {
@@ -289,7 +281,6 @@ static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdL
 
 }  // namespace geoa3
 
-extern "C" __attribute__((visibility("default"))) void geoa3_debug_read(long long* out) { cudaMemcpyFromSymbol(out, geoa3::g_dbg, 64); }
 
 extern "C" int geoa3_kappa_loss_fwd(const float* pc, const float* normal, const int32_t* jstar,
                                     const int32_t* nbr, int k, const float* d_a2o, const float* d_o2a,
