@@ -23,7 +23,8 @@ namespace geoa3 {
 
 constexpr int KNN_THREADS = 128;
 constexpr int KNN_CHUNK = 2048;  // candidates per shared-memory pass
-constexpr int KNN_QDEPTH = 8;    // queue slots per thread
+constexpr int KNN_QDEPTH = 40;   // queue slots per thread (indices only; distances are recomputed at drain):
+                                 // drained when > 8 are pending, and one 32-candidate group adds at most 32
 
 template <int K>
 struct TopK {
@@ -58,7 +59,6 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   __shared__ __align__(16) float sx[KNN_CHUNK];
   __shared__ __align__(16) float sy[KNN_CHUNK];
   __shared__ __align__(16) float sz[KNN_CHUNK];
-  __shared__ float qd[KNN_QDEPTH][KNN_THREADS];
   __shared__ int qj[KNN_QDEPTH][KNN_THREADS];
 
   const int cloud = blockIdx.y;
@@ -89,46 +89,81 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   do {
   top.init();
   float tau = tau0;
-  int cnt = 0;
+  // per-thread queue of passing candidate indices: qp walks down column `tid` of qj; the hot loop only
+  // does "compare, predicated store, predicated pointer bump" per candidate
+  // 32-bit shared-window address of this thread's queue column, kept in ONE register: the compiler otherwise
+  // re-materialises the base (3 extra predicated instructions per candidate)
+  const unsigned q0 = (unsigned)__cvta_generic_to_shared(&qj[0][tid]);
+  constexpr unsigned QSTRIDE = KNN_THREADS * sizeof(int);
+  unsigned qa = q0;
+  int c0 = 0;
 
   auto drain = [&]() {
+    const int cnt = (int)((qa - q0) / QSTRIDE);
     const int mx = __reduce_max_sync(0xffffffffu, cnt);
     for (int r = 0; r < mx; ++r) {
       // lanes without an r-th entry feed +inf, which the network leaves in the carry
-      const float x = r < cnt ? qd[r][tid] : __int_as_float(0x7f800000);
-      const int xi = r < cnt ? qj[r][tid] : -1;
+      float x = __int_as_float(0x7f800000);
+      int xi = -1;
+      if (r < cnt) {
+        xi = qj[r][tid];
+        const int l = xi - c0;  // the queue is drained before the staged chunk is replaced
+        x = dist2(sx[l], sy[l], sz[l], qx, qy, qz);  // bit-identical to the packed evaluation
+      }
       top.insert(x, xi);
     }
-    cnt = 0;
+    qa = q0;
     tau = fminf(tau0, top.tau());
   };
 
-  for (int c0 = 0; c0 < m; c0 += KNN_CHUNK) {
+  for (c0 = 0; c0 < m; c0 += KNN_CHUNK) {
     const int cn = min(KNN_CHUNK, m - c0);
-    const int cn4 = (cn + 3) & ~3;
+    const int cn32 = (cn + 31) & ~31;
     __syncthreads();
-    for (int t = tid; t < cn4; t += KNN_THREADS) {
+    for (int t = tid; t < cn32; t += KNN_THREADS) {
       const bool ok = t < cn;
-      sx[t] = ok ? cbase[c0 + t] : __int_as_float(0x7f800000);  // +inf padding never passes d < tau
+      sx[t] = ok ? cbase[c0 + t] : __int_as_float(0x7f800000);  // +inf padding: d = +inf never passes
       sy[t] = ok ? cbase[m + c0 + t] : 0.f;
       sz[t] = ok ? cbase[2 * m + c0 + t] : 0.f;
     }
     __syncthreads();
-    for (int j = 0; j < cn4; j += 4) {
-      const float4 cx = *reinterpret_cast<const float4*>(sx + j);
-      const float4 cy = *reinterpret_cast<const float4*>(sy + j);
-      const float4 cz = *reinterpret_cast<const float4*>(sz + j);
-      const float2 d01 = dist2x2(make_float2(cx.x, cx.y), make_float2(cy.x, cy.y), make_float2(cz.x, cz.y), nqx, nqy, nqz);
-      const float2 d23 = dist2x2(make_float2(cx.z, cx.w), make_float2(cy.z, cy.w), make_float2(cz.z, cz.w), nqx, nqy, nqz);
+    // The alu pipe (compares, selects, integer adds) is half as wide as the fma pipe, so the per-candidate
+    // bookkeeping is reduced to ONE alu op: s = d - tau is formed on the fma pipe (its sign is exact) and a
+    // funnel shift pushes the sign bit into a 32-candidate pass mask.  Set bits are expanded into the index
+    // queue once per 32 candidates (a short divergent loop, ~2% of the candidates pass).
+    for (int j = 0; j < cn32; j += 32) {
+      unsigned mask = 0u;
+      const float2 ntau = make_float2(-tau, -tau);
+#pragma unroll
+      for (int u = 0; u < 32; u += 8) {
+        const float4 cxa = *reinterpret_cast<const float4*>(sx + j + u), cxb = *reinterpret_cast<const float4*>(sx + j + u + 4);
+        const float4 cya = *reinterpret_cast<const float4*>(sy + j + u), cyb = *reinterpret_cast<const float4*>(sy + j + u + 4);
+        const float4 cza = *reinterpret_cast<const float4*>(sz + j + u), czb = *reinterpret_cast<const float4*>(sz + j + u + 4);
+        const float2 s01 = __fadd2_rn(dist2x2(make_float2(cxa.x, cxa.y), make_float2(cya.x, cya.y), make_float2(cza.x, cza.y), nqx, nqy, nqz), ntau);
+        const float2 s23 = __fadd2_rn(dist2x2(make_float2(cxa.z, cxa.w), make_float2(cya.z, cya.w), make_float2(cza.z, cza.w), nqx, nqy, nqz), ntau);
+        const float2 s45 = __fadd2_rn(dist2x2(make_float2(cxb.x, cxb.y), make_float2(cyb.x, cyb.y), make_float2(czb.x, czb.y), nqx, nqy, nqz), ntau);
+        const float2 s67 = __fadd2_rn(dist2x2(make_float2(cxb.z, cxb.w), make_float2(cyb.z, cyb.w), make_float2(czb.z, czb.w), nqx, nqy, nqz), ntau);
+        // d < tau  <=>  sign(d - tau) set  (d = +inf padding gives +inf or the positive canonical NaN)
+        mask = __funnelshift_l(__float_as_uint(s01.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s01.y), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s23.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s23.y), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s45.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s45.y), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s67.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s67.y), mask, 1);
+      }
       const int jj = c0 + j;
-      if (d01.x < tau) { qd[cnt][tid] = d01.x; qj[cnt][tid] = jj; ++cnt; }
-      if (d01.y < tau) { qd[cnt][tid] = d01.y; qj[cnt][tid] = jj + 1; ++cnt; }
-      if (d23.x < tau) { qd[cnt][tid] = d23.x; qj[cnt][tid] = jj + 2; ++cnt; }
-      if (d23.y < tau) { qd[cnt][tid] = d23.y; qj[cnt][tid] = jj + 3; ++cnt; }
-      if (__any_sync(0xffffffffu, cnt > KNN_QDEPTH - 4)) drain();
+      while (mask) {  // bit 31 is candidate jj, bit 0 is candidate jj+31: ascending index = descending bit
+        const int t = __clz(mask);
+        mask &= ~(0x80000000u >> t);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(jj + t) : "memory");
+        qa += QSTRIDE;
+      }
+      if (__any_sync(0xffffffffu, qa > q0 + 8 * QSTRIDE)) drain();
     }
+    drain();  // queue entries index the staged chunk: empty it before the chunk is replaced
   }
-  drain();
   // fewer than K candidates under the hinted bound => the bound was not valid for this query: redo unhinted
   rescan = __syncthreads_or((qi < n) && top.i[K - 1] < 0 && tau0 != __int_as_float(0x7f800000));
   tau0 = __int_as_float(0x7f800000);
