@@ -22,9 +22,9 @@
 namespace geoa3 {
 
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_CHUNK = 2048;  // candidates per shared-memory pass
-constexpr int KNN_QDEPTH = 40;   // queue slots per thread (indices only; distances are recomputed at drain):
-                                 // drained when > 8 are pending, and one 32-candidate group adds at most 32
+constexpr int KNN_CHUNK = 1024;  // candidates per shared-memory pass (12 KB; static smem stays under 48 KB)
+constexpr int KNN_QDEPTH = 56;   // queue slots per thread (indices only; distances are recomputed at drain):
+                                 // drained when > 24 are pending, and one 32-candidate group adds at most 32
 
 template <int K>
 struct TopK {
@@ -53,7 +53,7 @@ struct TopK {
 };
 
 template <int K>
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, K <= 17 ? 6 : 4)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n, int m, int kout, int drop,
            const int32_t* hint, int hint_k, int32_t* idx_out, float* __restrict__ dist_out) {
   __shared__ __align__(16) float sx[KNN_CHUNK];
@@ -70,25 +70,16 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   const float qx = qbase[qq], qy = qbase[n + qq], qz = qbase[2 * n + qq];
   const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
 
-  // hinted start threshold: max exact distance to the hinted candidates and to the point of the same index
-  // (the self match of a self-query), nudged one ulp up so that the strict test below admits equality.
+  // hinted start threshold (evaluated below, once the first candidate chunk sits in shared memory)
   float tau0 = __int_as_float(0x7f800000);
-  if (hint != nullptr && hint_k + 1 >= K) {
-    const int32_t* h = hint + ((size_t)cloud * n + qq) * hint_k;  // may alias idx_out: own row, read before write
-    const int s0 = min(qq, m - 1);
-    float mx = dist2(cbase[s0], cbase[m + s0], cbase[2 * m + s0], qx, qy, qz);
-    for (int t = 0; t < hint_k; ++t) {
-      const int j = min(max(h[t], 0), m - 1);
-      mx = fmaxf(mx, dist2(cbase[j], cbase[m + j], cbase[2 * m + j], qx, qy, qz));
-    }
-    if (mx < 3.0e38f) tau0 = __uint_as_float(__float_as_uint(mx) + 1u);
-  }
+  const bool use_hint = hint != nullptr && hint_k + 1 >= K;
 
   TopK<K> top;
   bool rescan = false;
   do {
   top.init();
   float tau = tau0;
+  bool hint_pending = use_hint && !rescan;
   // per-thread queue of passing candidate indices: qp walks down column `tid` of qj; the hot loop only
   // does "compare, predicated store, predicated pointer bump" per candidate
   // 32-bit shared-window address of this thread's queue column, kept in ONE register: the compiler otherwise
@@ -127,6 +118,22 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
       sz[t] = ok ? cbase[2 * m + c0 + t] : 0.f;
     }
     __syncthreads();
+    if (hint_pending) {
+      // tau0 = max exact distance to the hinted candidates and to the point of the same index (the self match
+      // of a self-query), nudged one ulp up so that the strict test admits equality.  Candidates of the staged
+      // chunk are read from shared memory, the rest (m > KNN_CHUNK only) from global memory.
+      hint_pending = false;
+      const int32_t* h = hint + ((size_t)cloud * n + qq) * hint_k;  // may alias idx_out: own row, read before write
+      auto cand_d = [&](int j) {
+        j = min(max(j, 0), m - 1);
+        return j < cn ? dist2(sx[j], sy[j], sz[j], qx, qy, qz)
+                      : dist2(cbase[j], cbase[m + j], cbase[2 * m + j], qx, qy, qz);
+      };
+      float mx = cand_d(qq);
+      for (int t = 0; t < hint_k; ++t) mx = fmaxf(mx, cand_d(h[t]));
+      if (mx < 3.0e38f) tau0 = __uint_as_float(__float_as_uint(mx) + 1u);
+      tau = tau0;
+    }
     // The alu pipe (compares, selects, integer adds) is half as wide as the fma pipe, so the per-candidate
     // bookkeeping is reduced to ONE alu op: s = d - tau is formed on the fma pipe (its sign is exact) and a
     // funnel shift pushes the sign bit into a 32-candidate pass mask.  Set bits are expanded into the index
@@ -134,7 +141,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
     for (int j = 0; j < cn32; j += 32) {
       unsigned mask = 0u;
       const float2 ntau = make_float2(-tau, -tau);
-#pragma unroll
+#pragma unroll 2
       for (int u = 0; u < 32; u += 8) {
         const float4 cxa = *reinterpret_cast<const float4*>(sx + j + u), cxb = *reinterpret_cast<const float4*>(sx + j + u + 4);
         const float4 cya = *reinterpret_cast<const float4*>(sy + j + u), cyb = *reinterpret_cast<const float4*>(sy + j + u + 4);
@@ -160,7 +167,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(jj + t) : "memory");
         qa += QSTRIDE;
       }
-      if (__any_sync(0xffffffffu, qa > q0 + 8 * QSTRIDE)) drain();
+      if (__any_sync(0xffffffffu, qa > q0 + (KNN_QDEPTH - 32) * QSTRIDE)) drain();
     }
     drain();  // queue entries index the staged chunk: empty it before the chunk is replaced
   }
