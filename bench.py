@@ -120,12 +120,17 @@ def time_events(fn, iters, warm):
 
 
 def kernel_breakdown(pc_ori, nrm, adv, k):
-    """CUDA-event time of each own kernel of the loss path at the bench batch (µs, mean of 10)."""
+    """CUDA-event time of each own kernel of the loss path at the bench batch (µs, mean of 10), in the exact
+    configuration the attack step launches them: 1-NN seeded and kNN threshold hinted with the previous
+    step's indices (here: the indices of a cloud one Adam step away)."""
     from geoa3_b200 import ops
 
     b, _, n = adv.shape
-    d1, js, d2, is_ = ops.nn_pair(adv, pc_ori)
-    nbr = ops.knn(adv, adv, k + 1, drop=1)[0]
+    prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
+    _, hj, _, hi = ops.nn_pair(prev, pc_ori)
+    hn = ops.knn(prev, prev, k + 1, drop=1)[0]
+    d1, js, d2, is_ = ops.nn_pair(adv, pc_ori, hint_a2o=hj, hint_o2a=hi)
+    nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
     nbr_o = ops.knn(pc_ori, pc_ori, k + 1, drop=1)[0]
     ko = ops.kappa_loss_fwd(pc_ori, normal=nrm, nbr=nbr_o)["kappa"]
 
@@ -136,8 +141,8 @@ def kernel_breakdown(pc_ori, nrm, adv, k):
     out = fwd()
     g = torch.full((b,), 1.0 / b, device=adv.device)
     t = {
-        "nn_pair": time_events(lambda: ops.nn_pair(adv, pc_ori), 10, 3),
-        "knn": time_events(lambda: ops.knn(adv, adv, k + 1, drop=1), 10, 3),
+        "nn_pair": time_events(lambda: ops.nn_pair(adv, pc_ori, hint_a2o=hj, hint_o2a=hi), 10, 3),
+        "knn": time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), 10, 3),
         "kappa_loss_fwd": time_events(fwd, 10, 3),
         "loss_bwd": time_events(lambda: ops.loss_bwd(adv, ori=pc_ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"],
                                                      kappa_ori=ko, jstar=js, istar=is_, nbr=nbr, hd_arg=out["hd_arg"],

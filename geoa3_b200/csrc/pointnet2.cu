@@ -261,6 +261,52 @@ csr_gather_grad_kernel(const float* __restrict__ grad_out, const float* __restri
   }
 }
 
+// Cooperative variant for many channels (the feature-grouping gradient, C >= 8): the CSR of one cloud is staged
+// ONCE per CTA in shared memory (entries as uint16) and reused for GG2_CC channels; each channel's grad_out row
+// is staged with 16-byte async copies; eight lanes share a target (lane-strided partial sums + a fixed shuffle
+// tree), which bounds the damage of the long segments ball-query padding creates (the first index of a
+// sparse ball is repeated up to nsample times).  Everything the inner loop touches is in shared memory.
+// (Position-balanced segmented-reduction, double-buffered and bank-swizzled variants were measured slower on
+// B200 at the SSG shapes — see DESIGN.md §7; this op is latency-bound per CTA, not bandwidth-bound, today.)
+constexpr int GG2_THREADS = 256;
+constexpr int GG2_CC = 8;
+
+__global__ void __launch_bounds__(GG2_THREADS)
+csr_gather_grad_coop_kernel(const float* __restrict__ grad_out, const int* __restrict__ ws, int c, int n, int E,
+                            float* __restrict__ grad_points) {
+  extern __shared__ __align__(16) unsigned char gg2_smem[];
+  float* s_go = reinterpret_cast<float*>(gg2_smem);                            // E floats
+  int* s_offs = reinterpret_cast<int*>(gg2_smem + (size_t)E * 4);              // n+1 ints
+  uint16_t* s_ent = reinterpret_cast<uint16_t*>(s_offs + ((n + 1 + 3) & ~3));  // E uint16
+  const int cloud = blockIdx.y, c0 = blockIdx.x * GG2_CC, cc = min(GG2_CC, c - c0), tid = threadIdx.x;
+  const int* offs = ws + (size_t)cloud * (n + 1 + E);
+  const int* ent = offs + n + 1;
+  for (int i = tid; i <= n; i += GG2_THREADS) s_offs[i] = offs[i];
+  for (int i = tid; i < E; i += GG2_THREADS) s_ent[i] = (uint16_t)ent[i];
+  const int sub = tid & 7, grp = tid >> 3;  // 8 lanes per target, 32 targets in flight per CTA
+  for (int l = 0; l < cc; ++l) {
+    const float* go = grad_out + ((size_t)cloud * c + c0 + l) * E;
+    __syncthreads();  // previous channel fully consumed (and the CSR staged, first time round)
+    for (int i = tid * 4; i < E; i += GG2_THREADS * 4) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(s_go + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(go + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float* gp = grad_points + ((size_t)cloud * c + c0 + l) * n;
+    for (int p = grp; p < n; p += GG2_THREADS / 8) {
+      const int e1 = s_offs[p + 1];
+      float acc = 0.f;
+      for (int t = s_offs[p] + sub; t < e1; t += 8) acc += s_go[s_ent[t]];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (sub == 0) gp[p] = acc;
+    }
+  }
+}
+
 // ============================================================================ gather_points (+grad)
 __global__ void gather_points_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx, int c, int n,
                                      int m, float* __restrict__ out) {
@@ -349,6 +395,19 @@ static int run_csr_grad(const float* grad_out, const float* weight, const int32_
   csr_global_kernel<<<b, CSRG_THREADS, sm1, s>>>(idx, E, n, W, (int*)workspace);
   int err = GEOA3_LAUNCH_RESULT();
   if (err) return err;
+  const size_t coop_smem = (size_t)E * 4 + (size_t)((n + 1 + 3) & ~3) * 4 + (size_t)E * 2;
+  if (!weight && e_div == 1 && c >= GG2_CC && (E & 3) == 0 && E <= 65536 && coop_smem <= 110 * 1024) {
+    static bool coop_attr = false;
+    if (!coop_attr) {
+      cudaError_t e = cudaFuncSetAttribute(csr_gather_grad_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           110 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      coop_attr = true;
+    }
+    csr_gather_grad_coop_kernel<<<dim3(ceil_div(c, GG2_CC), b), GG2_THREADS, coop_smem, s>>>(
+        grad_out, (const int*)workspace, c, n, E, grad_points);
+    return GEOA3_LAUNCH_RESULT();
+  }
   const int Eg = E / e_div;
   int tile = Eg;
   if ((size_t)Eg * 4 > 96 * 1024) {

@@ -31,13 +31,41 @@ def timeit(fn, iters=20, warm=5, flush=None):
     return ts[len(ts) // 2], ts[0]
 
 
+def sweep():
+    """kNN + kappa kernels at B=64, N in {1024,4096,10000}, k in {16,32} (BASELINE config[3])."""
+    B = 64
+    for n in (1024, 4096, 10000):
+        pc, nr, _ = synth.make_batch(16, n)
+        ori = torch.from_numpy(np.tile(pc, (4, 1, 1))).cuda()
+        nrm = torch.from_numpy(np.tile(nr, (4, 1, 1))).cuda()
+        adv = ori + torch.from_numpy(synth.make_offsets(B, n)).cuda()
+        prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
+        for k in (16, 32):
+            hn = ops.knn(prev, prev, k + 1, drop=1)[0]
+            t_knn = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1), iters=5, warm=2)
+            t_hint = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), iters=5, warm=2)
+            nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
+            assert torch.equal(nbr, ops.knn(adv, adv, k + 1, drop=1)[0])
+            _, js, _, _ = ops.nn_pair(adv, ori)
+            t_kap = timeit(lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr), iters=5, warm=2)
+            byts = (28 + 4 * k) * B * n
+            flop = 8.0 * B * n * n
+            print(json.dumps(dict(what="curvature_sweep", B=B, n=n, k=k, knn_us=round(t_knn[0], 1),
+                                  knn_hinted_us=round(t_hint[0], 1), kappa_us=round(t_kap[0], 1),
+                                  hbm_frac=round(byts / ((t_hint[0] + t_kap[0]) * 1e-6) / 6555.2e9, 5),
+                                  fp32_tflops_hinted=round(flop / (t_hint[0] * 1e-6) / 1e12, 2))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--b", type=int, default=250)
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--pn2", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config[3]: curvature-loss scaling sweep")
     a = ap.parse_args()
+    if a.sweep:
+        return sweep()
     b, n, k = a.b, a.n, a.k
     pc, nr, _ = synth.make_batch(min(b, 20), n)
     reps = (b + pc.shape[0] - 1) // pc.shape[0]
