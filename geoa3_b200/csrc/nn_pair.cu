@@ -13,6 +13,14 @@
 // Only when that fires does the thread walk the 8 candidates with the exact lexicographic rule
 // (d < best) or (d == best and j < argbest), so the result is the same (min, lowest index) the plain
 // ascending scan produces — for ANY seed; a bad seed only costs speed.
+//
+// Conservative filter.  The question "can any of these 8 candidates reach best?" does not need the pinned
+// arithmetic, only a value that never under-reports by more than a known bound.  The hot loop therefore
+// evaluates t = |c|^2 - 2 q.c (three FFMA2 per two candidates instead of six packed ops; |c|^2 is staged
+// next to the coordinates) and tests  min t <= best - |q|^2 + margin,  margin = 2^-17 * max(|q|^2, max|c|^2)
+// (~4x the worst-case sum of the rounding errors of both formulas).  Everything that
+// passes is re-evaluated with the pinned fma chain before it may touch (best, argbest), so the outputs are
+// bit-identical to the plain scan; the filter only decides what is worth evaluating exactly.
 #include "common.cuh"
 
 namespace geoa3 {
@@ -30,6 +38,8 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
   __shared__ __align__(16) float sx[NN_CHUNK];
   __shared__ __align__(16) float sy[NN_CHUNK];
   __shared__ __align__(16) float sz[NN_CHUNK];
+  __shared__ __align__(16) float sw[NN_CHUNK];  // |c|^2
+  __shared__ float s_c2max[NN_THREADS / 32];
 
   const int cloud = blockIdx.y;
   int tile = blockIdx.x;
@@ -45,7 +55,22 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
   const int32_t* hint = dir1 ? hint_o2a : hint_a2o;  // may alias iout: each thread reads its own slot first
   if (hint) hint += (size_t)cloud * nq;
 
-  float2 nqx[Q], nqy[Q], nqz[Q];
+  // upper bound of |c|^2 over the whole candidate cloud (enters the filter margin)
+  float c2max = 0.f;
+  for (int t = threadIdx.x; t < nc; t += NN_THREADS) {
+    const float x = cbase[t], y = cbase[nc + t], z = cbase[2 * nc + t];
+    c2max = fmaxf(c2max, x * x + y * y + z * z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c2max = fmaxf(c2max, __shfl_xor_sync(0xffffffffu, c2max, o));
+  if ((threadIdx.x & 31) == 0) s_c2max[threadIdx.x >> 5] = c2max;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NN_THREADS / 32; ++i) c2max = fmaxf(c2max, s_c2max[i]);
+
+  float qx[Q], qy[Q], qz[Q];
+  float2 ax[Q], ay[Q], az[Q];  // -2q, both halves
+  float qq2[Q], margin[Q], thr[Q];
   float best[Q];
   int bi[Q];
   int qi[Q];
@@ -54,13 +79,17 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
     qi[q] = tile * (NN_THREADS * Q) + q * NN_THREADS + threadIdx.x;
     const int qq = min(qi[q], nq - 1);
     const float x = qbase[qq], y = qbase[nq + qq], z = qbase[2 * nq + qq];
-    nqx[q] = make_float2(-x, -x);
-    nqy[q] = make_float2(-y, -y);
-    nqz[q] = make_float2(-z, -z);
+    qx[q] = x; qy[q] = y; qz[q] = z;
+    ax[q] = make_float2(-2.f * x, -2.f * x);
+    ay[q] = make_float2(-2.f * y, -2.f * y);
+    az[q] = make_float2(-2.f * z, -2.f * z);
+    qq2[q] = x * x + y * y + z * z;
+    margin[q] = 7.62939453125e-6f * 1.001f * fmaxf(qq2[q], c2max);  // 2^-17 * R^2
     int seed = hint ? hint[qq] : qq;
     seed = min(max(seed, 0), nc - 1);
-    best[q] = dist2(cbase[seed], cbase[nc + seed], cbase[2 * nc + seed], x, y, z);  // == packed result, bit for bit
+    best[q] = dist2(cbase[seed], cbase[nc + seed], cbase[2 * nc + seed], x, y, z);
     bi[q] = seed;
+    thr[q] = (best[q] - qq2[q]) + margin[q];
   }
 
   for (int c0 = 0; c0 < nc; c0 += NN_CHUNK) {
@@ -69,29 +98,44 @@ nn_pair_kernel(const float* __restrict__ adv, const float* __restrict__ ori, int
     __syncthreads();
     for (int t = threadIdx.x; t < cn8; t += NN_THREADS) {
       const bool ok = t < cn;
-      // padding candidates sit at +inf: their distance is +inf, never <= a finite best
-      sx[t] = ok ? cbase[c0 + t] : NN_INF;
-      sy[t] = ok ? cbase[nc + c0 + t] : 0.f;
-      sz[t] = ok ? cbase[2 * nc + c0 + t] : 0.f;
+      // padding candidates sit far away (finite, so the filter never sees inf*0): they can never pass
+      const float x = ok ? cbase[c0 + t] : 1e18f, y = ok ? cbase[nc + c0 + t] : 0.f, z = ok ? cbase[2 * nc + c0 + t] : 0.f;
+      sx[t] = x; sy[t] = y; sz[t] = z;
+      sw[t] = x * x + y * y + z * z;
     }
     __syncthreads();
     for (int j = 0; j < cn8; j += 8) {
       const float4 cxa = *reinterpret_cast<const float4*>(sx + j), cxb = *reinterpret_cast<const float4*>(sx + j + 4);
       const float4 cya = *reinterpret_cast<const float4*>(sy + j), cyb = *reinterpret_cast<const float4*>(sy + j + 4);
       const float4 cza = *reinterpret_cast<const float4*>(sz + j), czb = *reinterpret_cast<const float4*>(sz + j + 4);
-      const int jj = c0 + j;
+      const float4 cwa = *reinterpret_cast<const float4*>(sw + j), cwb = *reinterpret_cast<const float4*>(sw + j + 4);
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const float2 d01 = dist2x2(make_float2(cxa.x, cxa.y), make_float2(cya.x, cya.y), make_float2(cza.x, cza.y), nqx[q], nqy[q], nqz[q]);
-        const float2 d23 = dist2x2(make_float2(cxa.z, cxa.w), make_float2(cya.z, cya.w), make_float2(cza.z, cza.w), nqx[q], nqy[q], nqz[q]);
-        const float2 d45 = dist2x2(make_float2(cxb.x, cxb.y), make_float2(cyb.x, cyb.y), make_float2(czb.x, czb.y), nqx[q], nqy[q], nqz[q]);
-        const float2 d67 = dist2x2(make_float2(cxb.z, cxb.w), make_float2(cyb.z, cyb.w), make_float2(czb.z, czb.w), nqx[q], nqy[q], nqz[q]);
-        const float mn = fminf(fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)), fminf(fminf(d45.x, d45.y), fminf(d67.x, d67.y)));
-        if (mn <= best[q]) {  // rare: exact lexicographic update over the 8 candidates
-          const float dd[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};
+        // t = |c|^2 - 2 q.c  for 8 candidates: 12 FFMA2
+        float2 t01 = __ffma2_rn(az[q], make_float2(cza.x, cza.y), make_float2(cwa.x, cwa.y));
+        float2 t23 = __ffma2_rn(az[q], make_float2(cza.z, cza.w), make_float2(cwa.z, cwa.w));
+        float2 t45 = __ffma2_rn(az[q], make_float2(czb.x, czb.y), make_float2(cwb.x, cwb.y));
+        float2 t67 = __ffma2_rn(az[q], make_float2(czb.z, czb.w), make_float2(cwb.z, cwb.w));
+        t01 = __ffma2_rn(ay[q], make_float2(cya.x, cya.y), t01);
+        t23 = __ffma2_rn(ay[q], make_float2(cya.z, cya.w), t23);
+        t45 = __ffma2_rn(ay[q], make_float2(cyb.x, cyb.y), t45);
+        t67 = __ffma2_rn(ay[q], make_float2(cyb.z, cyb.w), t67);
+        t01 = __ffma2_rn(ax[q], make_float2(cxa.x, cxa.y), t01);
+        t23 = __ffma2_rn(ax[q], make_float2(cxa.z, cxa.w), t23);
+        t45 = __ffma2_rn(ax[q], make_float2(cxb.x, cxb.y), t45);
+        t67 = __ffma2_rn(ax[q], make_float2(cxb.z, cxb.w), t67);
+        const float mn = fminf(fminf(fminf(t01.x, t01.y), fminf(t23.x, t23.y)), fminf(fminf(t45.x, t45.y), fminf(t67.x, t67.y)));
+        if (mn <= thr[q]) {  // rare: pinned arithmetic + exact lexicographic update over the 8 candidates
+          const float cx8[8] = {cxa.x, cxa.y, cxa.z, cxa.w, cxb.x, cxb.y, cxb.z, cxb.w};
+          const float cy8[8] = {cya.x, cya.y, cya.z, cya.w, cyb.x, cyb.y, cyb.z, cyb.w};
+          const float cz8[8] = {cza.x, cza.y, cza.z, cza.w, czb.x, czb.y, czb.z, czb.w};
+          const int jj = c0 + j;
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (dd[t] < best[q] || (dd[t] == best[q] && jj + t < bi[q])) { best[q] = dd[t]; bi[q] = jj + t; }
+          for (int t = 0; t < 8; ++t) {
+            const float d = dist2(cx8[t], cy8[t], cz8[t], qx[q], qy[q], qz[q]);
+            if (d < best[q] || (d == best[q] && jj + t < bi[q])) { best[q] = d; bi[q] = jj + t; }
+          }
+          thr[q] = (best[q] - qq2[q]) + margin[q];
         }
       }
     }

@@ -1,165 +1,140 @@
-"""Drop-in for pointnet2_ops/pointnet2_utils.py of the reference: the six autograd Functions with
-their `.apply` aliases and the QueryAndGroup / GroupAll modules — same names, argument order, dtypes
-(float32 features / int32 indices), mark_non_differentiable and backward return conventions
-(reference lines cited per class).  The native side is libgeoa3_b200.so via `_ext`; there is no JIT
-compile and no CPU fallback."""
+"""B200 drop-in for the reference's pointnet2_ops/pointnet2_utils.py.
+
+Public surface (identical names, argument order, dtypes and autograd conventions; reference lines in brackets):
+
+    furthest_point_sample(xyz (B,N,3) f32, npoint) -> (B,npoint) i32, non-differentiable        [:34-65]
+    gather_operation(features (B,C,N), idx (B,npoint) i32) -> (B,C,npoint)                      [:68-101]
+    three_nn(unknown (B,n,3), known (B,m,3)) -> (dist (B,n,3), idx (B,n,3) i32), non-diff.     [:104-136]
+    three_interpolate(features (B,c,m), idx (B,n,3), weight (B,n,3)) -> (B,c,n)                [:139-191]
+    grouping_operation(features (B,C,N), idx (B,npoint,nsample) i32) -> (B,C,npoint,nsample)   [:194-240]
+    ball_query(radius, nsample, xyz (B,N,3), new_xyz (B,npoint,3)) -> (B,npoint,nsample) i32   [:243-276]
+    QueryAndGroup(radius, nsample, use_xyz=True), GroupAll(use_xyz=True)                        [:279-379]
+
+Note the Python order of ball_query's arguments differs from the native one (new_xyz, xyz, radius, nsample)
+[:265].  Backward conventions kept: index-producing ops return `()`; GatherOperation returns (grad, None);
+GroupingOperation / ThreeInterpolate return zero tensors for their index / weight inputs.  The native side
+is libgeoa3_b200.so through `_ext`; gradients are deterministic gathers instead of float atomics.
+There is no JIT build and no CPU path: CPU tensors raise RuntimeError.
+"""
 import torch
-import torch.nn as nn
+from torch import nn
 from torch.autograd import Function
 
 from . import _ext
 
 
-class FurthestPointSampling(Function):
-    """pointnet2_utils.py:34-62. xyz (B,N,3) float32, npoint -> (B,npoint) int32, non-differentiable."""
+class _IndexOp(Function):
+    """Base of the ops whose outputs are indices: nothing to differentiate."""
 
     @staticmethod
-    def forward(ctx, xyz, npoint):
-        out = _ext.furthest_point_sampling(xyz, npoint)
-        ctx.mark_non_differentiable(out)
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, *unused_grads):
         return ()
 
 
-furthest_point_sample = FurthestPointSampling.apply
+class FurthestPointSampling(_IndexOp):
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        picked = _ext.furthest_point_sampling(xyz, npoint)
+        ctx.mark_non_differentiable(picked)
+        return picked
+
+
+class BallQuery(_IndexOp):
+    @staticmethod
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        members = _ext.ball_query(new_xyz, xyz, radius, nsample)
+        ctx.mark_non_differentiable(members)
+        return members
+
+
+class ThreeNN(_IndexOp):
+    @staticmethod
+    def forward(ctx, unknown, known):
+        sq_dist, nearest = _ext.three_nn(unknown, known)
+        dist = sq_dist.sqrt()
+        ctx.mark_non_differentiable(dist, nearest)
+        return dist, nearest
 
 
 class GatherOperation(Function):
-    """pointnet2_utils.py:68-98. features (B,C,N), idx (B,npoint) -> (B,C,npoint)."""
-
     @staticmethod
     def forward(ctx, features, idx):
-        ctx.save_for_backward(idx, features)
+        ctx.save_for_backward(idx)
+        ctx.n_src = features.size(2)
         return _ext.gather_points(features, idx)
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, features = ctx.saved_tensors
-        N = features.size(2)
-        grad_features = _ext.gather_points_grad(grad_out.contiguous(), idx, N)
-        return grad_features, None
-
-
-gather_operation = GatherOperation.apply
-
-
-class ThreeNN(Function):
-    """pointnet2_utils.py:104-133. unknown (B,n,3), known (B,m,3) -> dist (B,n,3) (sqrt of squared), idx (B,n,3)."""
-
-    @staticmethod
-    def forward(ctx, unknown, known):
-        dist2, idx = _ext.three_nn(unknown, known)
-        dist = torch.sqrt(dist2)
-        ctx.mark_non_differentiable(dist, idx)
-        return dist, idx
-
-    @staticmethod
-    def backward(ctx, grad_dist, grad_idx):
-        return ()
-
-
-three_nn = ThreeNN.apply
-
-
-class ThreeInterpolate(Function):
-    """pointnet2_utils.py:139-188. features (B,c,m), idx/weight (B,n,3) -> (B,c,n)."""
-
-    @staticmethod
-    def forward(ctx, features, idx, weight):
-        ctx.save_for_backward(idx, weight, features)
-        return _ext.three_interpolate(features, idx, weight)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, weight, features = ctx.saved_tensors
-        m = features.size(2)
-        grad_features = _ext.three_interpolate_grad(grad_out.contiguous(), idx, weight, m)
-        return grad_features, torch.zeros_like(idx), torch.zeros_like(weight)
-
-
-three_interpolate = ThreeInterpolate.apply
+        (idx,) = ctx.saved_tensors
+        return _ext.gather_points_grad(grad_out.contiguous(), idx, ctx.n_src), None
 
 
 class GroupingOperation(Function):
-    """pointnet2_utils.py:194-237. features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample)."""
-
     @staticmethod
     def forward(ctx, features, idx):
-        ctx.save_for_backward(idx, features)
+        ctx.save_for_backward(idx)
+        ctx.n_src = features.size(2)
         return _ext.group_points(features, idx)
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, features = ctx.saved_tensors
-        N = features.size(2)
-        grad_features = _ext.group_points_grad(grad_out.contiguous(), idx, N)
-        return grad_features, torch.zeros_like(idx)
+        (idx,) = ctx.saved_tensors
+        return _ext.group_points_grad(grad_out.contiguous(), idx, ctx.n_src), torch.zeros_like(idx)
 
 
-grouping_operation = GroupingOperation.apply
-
-
-class BallQuery(Function):
-    """pointnet2_utils.py:243-273. NOTE the Python argument order (radius, nsample, xyz, new_xyz) versus
-    the native (new_xyz, xyz, radius, nsample) (pointnet2_utils.py:265)."""
-
+class ThreeInterpolate(Function):
     @staticmethod
-    def forward(ctx, radius, nsample, xyz, new_xyz):
-        output = _ext.ball_query(new_xyz, xyz, radius, nsample)
-        ctx.mark_non_differentiable(output)
-        return output
+    def forward(ctx, features, idx, weight):
+        ctx.save_for_backward(idx, weight)
+        ctx.n_src = features.size(2)
+        return _ext.three_interpolate(features, idx, weight)
 
     @staticmethod
     def backward(ctx, grad_out):
-        return ()
+        idx, weight = ctx.saved_tensors
+        grad = _ext.three_interpolate_grad(grad_out.contiguous(), idx, weight, ctx.n_src)
+        return grad, torch.zeros_like(idx), torch.zeros_like(weight)
 
 
+furthest_point_sample = FurthestPointSampling.apply
+gather_operation = GatherOperation.apply
+three_nn = ThreeNN.apply
+three_interpolate = ThreeInterpolate.apply
+grouping_operation = GroupingOperation.apply
 ball_query = BallQuery.apply
 
 
+def _stack_xyz_and_features(grouped_xyz, grouped_features, use_xyz):
+    if grouped_features is None:
+        return grouped_xyz
+    return torch.cat([grouped_xyz, grouped_features], dim=1) if use_xyz else grouped_features
+
+
 class QueryAndGroup(nn.Module):
-    """Ball query + grouping (pointnet2_utils.py:279-333)."""
+    """Ball query around `new_xyz`, then gather coordinates (relative to the centroid) and features:
+    (B,N,3), (B,npoint,3), (B,C,N)|None -> (B, 3+C, npoint, nsample)."""
 
     def __init__(self, radius, nsample, use_xyz=True):
-        super(QueryAndGroup, self).__init__()
+        super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
 
     def forward(self, xyz, new_xyz, features=None):
-        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
-        grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)  # in place, as the reference (:317)
-
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            if self.use_xyz:
-                new_features = torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, C + 3, npoint, nsample)
-            else:
-                new_features = grouped_features
-        else:
+        members = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        rel = grouping_operation(xyz.transpose(1, 2).contiguous(), members)
+        rel -= new_xyz.transpose(1, 2).unsqueeze(-1)  # in place on the op's output, like the reference [:317]
+        if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            new_features = grouped_xyz
-        return new_features
+            return rel
+        return _stack_xyz_and_features(rel, grouping_operation(features, members), self.use_xyz)
 
 
 class GroupAll(nn.Module):
-    """Groups all features (pointnet2_utils.py:336-379); no native op involved."""
+    """One group holding every point: (B,N,3), _, (B,C,N)|None -> (B, 3+C, 1, N).  No native op involved."""
 
     def __init__(self, use_xyz=True):
-        super(GroupAll, self).__init__()
+        super().__init__()
         self.use_xyz = use_xyz
 
     def forward(self, xyz, new_xyz, features=None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is not None:
-            grouped_features = features.unsqueeze(2)
-            if self.use_xyz:
-                new_features = torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, 3 + C, 1, N)
-            else:
-                new_features = grouped_features
-        else:
-            new_features = grouped_xyz
-        return new_features
+        everything = xyz.transpose(1, 2).unsqueeze(2)
+        return _stack_xyz_and_features(everything, None if features is None else features.unsqueeze(2), self.use_xyz)

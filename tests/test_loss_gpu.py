@@ -263,3 +263,26 @@ def test_attack_state_hints_match_unhinted():
             tot.sum().backward()
             res.append((tot.detach().clone(), a.grad.clone()))
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (1e-3, 0.0), (1e3, 0.0), (1.0, 50.0), (1e-2, 7.0), (30.0, -200.0)])
+def test_nn_pair_filter_is_conservative(scale, shift):
+    """The hot loop only FILTERS with |c|^2 - 2q.c; every magnitude / offset must still give the oracle's
+    bit-exact (min, argmin): uncentred clouds make the expansion cancel catastrophically, near-duplicate
+    points make the margin matter."""
+    from geoa3_b200 import ops
+
+    rng = np.random.default_rng(11)
+    b, n, m = 3, 700, 900
+    base = rng.standard_normal((b, 3, m)).astype(np.float32)
+    ori = (base * scale + shift).astype(np.float32)
+    pick = rng.integers(0, m, (b, n))
+    adv = np.take_along_axis(ori, pick[:, None, :].repeat(3, 1), 2)
+    adv = (adv + rng.standard_normal((b, 3, n)).astype(np.float32) * np.float32(scale * 1e-6)).astype(np.float32)
+    adv[:, :, ::7] = np.take_along_axis(ori, pick[:, None, ::7].repeat(3, 1), 2)  # exact duplicates: ties at d = 0
+    od1, oj1 = O.nn1(adv, ori)
+    od2, oi2 = O.nn1(ori, adv)
+    for hint in (None, torch.zeros(b, n, dtype=torch.int32, device="cuda")):
+        d1, j1, d2, i2 = ops.nn_pair(cu(adv), cu(ori), hint_a2o=hint)
+        assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
+        assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
