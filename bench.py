@@ -104,13 +104,23 @@ def make_inputs(b, n, start):
     return pc, nr, lab
 
 
+_FLUSH = None
+
+
 def time_events(fn, iters, warm):
+    """Mean CUDA-event time of fn() in µs.  A 256 MB memset is queued in front of every timed call: it flushes
+    the 126 MB L2 and keeps the GPU busy while Python prepares the launch, so the interval between the two
+    events is the kernel itself, not the host-side launch latency."""
+    global _FLUSH
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _FLUSH.zero_()
         e0.record()
         fn()
         e1.record()
@@ -319,10 +329,13 @@ def main():
         alg_bytes = {"nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n, "kappa_loss_fwd": (36 + 4 * KNN) * b * n,
                      "loss_bwd": (56 + 4 * KNN) * b * n}[top]
         alg_flop = {"nn_pair": 16.0 * b * n * n, "knn": 8.0 * b * n * n}.get(top, 0.0)
+        # DRAM bytes per launch of each kernel from the committed `ncu --set full` captures (profiles/ncu_r1_summary.md:
+        # dram__bytes_read.sum + dram__bytes_write.sum at this exact shape); outputs mostly stay in the 126 MB L2
+        ncu_traffic = {"knn": 19.48e6, "nn_pair": 8.20e6, "kappa_loss_fwd": 26.66e6, "loss_bwd": 29.76e6}
         t_s = kb[top] * 1e-6
         achieved = alg_bytes / t_s / 1e9
         line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                            "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic.get(top), "peak_source": pk["source"],
                             "algorithmic_bytes_per_launch": alg_bytes,
                             "note": "distance kernels are FP32-issue bound (SURVEY §8d); see fp32",
                             "fp32": {"achieved_tflops": alg_flop / t_s / 1e12, "peak_tflops": pk["fp32_tflops"],
