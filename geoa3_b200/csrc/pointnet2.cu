@@ -15,6 +15,8 @@
 //  * group_points stages the gathered rows in shared memory (random 4-byte global gathers would cost a
 //    wavefront per sector) and writes float4 along nsample — the op is output-write bound.
 //  * scatter gradients (group / gather / three_interpolate) gather through a deterministic CSR (csr.cuh).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "csr.cuh"
 
@@ -184,9 +186,11 @@ group_points_kernel(const float* __restrict__ points, const int32_t* __restrict_
 constexpr int CSRG_THREADS = 512;
 
 __global__ void __launch_bounds__(CSRG_THREADS)
-csr_global_kernel(const int32_t* __restrict__ idx, int E, int n, int W, int* __restrict__ ws) {
+csr_global_kernel(const int32_t* __restrict__ idx, int E, int n, int W, int* __restrict__ ws,
+                  const int* __restrict__ fast_flag) {
   extern __shared__ __align__(16) int s_whist[];
   __shared__ int scan_scratch[CSRG_THREADS / 32 + 1];
+  if (fast_flag && *fast_flag == 0) return;  // the forward-order kernel handles this call (see fwd_order_ok_kernel)
   const int cloud = blockIdx.x;
   int* offs = ws + (size_t)cloud * (n + 1 + E);
   int* ent = offs + n + 1;
@@ -198,7 +202,9 @@ constexpr int GG_THREADS = 256;
 
 __global__ void __launch_bounds__(GG_THREADS)
 csr_gather_grad_kernel(const float* __restrict__ grad_out, const float* __restrict__ weight, const int* __restrict__ ws,
-                       int c, int n, int E, int e_div, int tile, float* __restrict__ grad_points) {
+                       int c, int n, int E, int e_div, int tile, float* __restrict__ grad_points,
+                       const int* __restrict__ fast_flag) {
+  if (fast_flag && *fast_flag == 0) return;
   // grad_out rows have E/e_div entries per channel (e_div = 3 for three_interpolate, where the three
   // (idx,weight) slots of one output share one grad_out value); weight (nullable) is [b][E].
   extern __shared__ __align__(16) float s_go[];  // one tile of the row
@@ -273,8 +279,9 @@ constexpr int GG2_CC = 8;
 
 __global__ void __launch_bounds__(GG2_THREADS)
 csr_gather_grad_coop_kernel(const float* __restrict__ grad_out, const int* __restrict__ ws, int c, int n, int E,
-                            float* __restrict__ grad_points) {
+                            float* __restrict__ grad_points, const int* __restrict__ fast_flag) {
   extern __shared__ __align__(16) unsigned char gg2_smem[];
+  if (fast_flag && *fast_flag == 0) return;
   float* s_go = reinterpret_cast<float*>(gg2_smem);                            // E floats
   int* s_offs = reinterpret_cast<int*>(gg2_smem + (size_t)E * 4);              // n+1 ints
   uint16_t* s_ent = reinterpret_cast<uint16_t*>(s_offs + ((n + 1 + 3) & ~3));  // E uint16
@@ -304,6 +311,109 @@ csr_gather_grad_coop_kernel(const float* __restrict__ grad_out, const int* __res
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       if (sub == 0) gp[p] = acc;
     }
+  }
+}
+
+// ============================================================================ group_points_grad, forward order
+// Ball-query index rows have a known shape: a strictly ascending prefix of distinct hits followed by copies of
+// the row's first index.  For such rows the scatter can run in FORWARD order with perfectly coalesced grad_out
+// reads and still be deterministic: warp w owns a contiguous block of rows and a private accumulator array in
+// shared memory; inside a 32-wide row slice all targets are distinct except the copies of the first index,
+// which are summed by a fixed shuffle tree and added once.  Per target the order is (warp block, row, slice)
+// + a fixed cross-warp reduction => bitwise reproducible, no atomics, no CSR, no sorting.
+// fwd_order_ok_kernel verifies the shape on the device (violations counter); if any row deviates this kernel
+// returns immediately and the generic CSR path (launched right after, predicated the other way) does the work.
+__global__ void fwd_order_ok_kernel(const int32_t* __restrict__ idx, int rows, int ns, int n, int* __restrict__ violations) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int32_t* r = idx + (size_t)row * ns;
+  const int p0 = r[0];
+  bool bad = p0 < 0 || p0 >= n;
+  // first position >= 1 holding p0 again = start of the padding suffix
+  int cnt = ns;
+  for (int k0 = 0; k0 < ns && cnt == ns; k0 += 32) {
+    const int k = k0 + lane;
+    const unsigned hit = __ballot_sync(0xffffffffu, k >= 1 && k < ns && r[k] == p0);
+    if (hit) cnt = k0 + __ffs(hit) - 1;
+  }
+  for (int k = 1 + lane; k < ns; k += 32) {
+    const int v = r[k];
+    if (k < cnt) bad |= !(v > r[k - 1]) || v >= n;
+    else bad |= v != p0;
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(violations, 1);
+}
+
+constexpr int GF_WARPS = 8;
+constexpr int GF_THREADS = GF_WARPS * 32;
+
+template <int CC>
+__global__ void __launch_bounds__(GF_THREADS)
+group_grad_fwd_order_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ idx, int c, int n, int m,
+                            int ns, float* __restrict__ grad_points, const int* __restrict__ violations) {
+  extern __shared__ __align__(16) float gf_acc[];  // [GF_WARPS][CC][n]
+  if (*violations != 0) return;
+  const int cloud = blockIdx.y, c0 = blockIdx.x * CC, cc = min(CC, c - c0);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < GF_WARPS * CC * n; i += GF_THREADS) gf_acc[i] = 0.f;
+  __syncthreads();
+  float* acc = gf_acc + (size_t)w * CC * n;
+  const int E = m * ns;
+  const int32_t* ix = idx + (size_t)cloud * E;
+  const float* go = grad_out + ((size_t)cloud * c + c0) * E;
+  const int rows_per_warp = (m + GF_WARPS - 1) / GF_WARPS;
+  const int j_beg = min(m, w * rows_per_warp), j_end = min(m, j_beg + rows_per_warp);
+  const int spr = (ns + 31) >> 5;                 // 32-wide slices per row
+  const int n_slices = (j_end - j_beg) * spr;
+  constexpr int D = 4;                            // slices fetched ahead: D*CC coalesced 128-byte loads in flight
+  const float* gol[CC];
+#pragma unroll
+  for (int l = 0; l < CC; ++l) gol[l] = go + (size_t)min(l, cc - 1) * E;
+  int row_e = j_beg * ns, k0 = 0;                 // running position of the next slice to fetch (no divisions)
+  for (int s0 = 0; s0 < n_slices; s0 += D) {
+    int pd[D], p0d[D];
+    float vd[D][CC];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const bool live = s0 + d < n_slices;
+      const int k = k0 + lane;
+      const bool valid = live && k < ns;
+      const int e = row_e + k;
+      pd[d] = valid ? ix[e] : -1;
+      p0d[d] = live ? ix[row_e] : -2;
+#pragma unroll
+      for (int l = 0; l < CC; ++l) vd[d][l] = valid ? __ldcs(gol[l] + e) : 0.f;
+      k0 += 32;
+      if (k0 >= ns) { k0 = 0; row_e += ns; }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int p = pd[d];
+      const bool valid = p >= 0;
+      const bool is0 = p == p0d[d];            // a copy of the row's first index (or that entry itself)
+      const unsigned m0 = __ballot_sync(0xffffffffu, is0);
+      const bool leader = is0 && (m0 & ((1u << lane) - 1u)) == 0u;   // lowest lane holding it
+      const bool rmw = valid && (!is0 || leader);
+      // control flow stays warp-uniform: the copies are ALWAYS summed by the fixed shuffle tree (a slice
+      // without copies just sums one value); a uniform-looking branch here makes the compiler wrap every
+      // shuffle in convergence barriers, which tripled the instruction count
+#pragma unroll
+      for (int l = 0; l < CC; ++l) {
+        const float v = vd[d][l];
+        const float t = warp_sum(is0 ? v : 0.f);
+        if (rmw) acc[l * n + p] += leader ? t : v;   // channels >= cc mirror channel cc-1 and are never written out
+      }
+      __syncwarp();  // the next slice / row may touch the same targets from other lanes
+    }
+  }
+  __syncthreads();
+  float* gp = grad_points + ((size_t)cloud * c + c0) * n;
+  for (int i = tid; i < cc * n; i += GF_THREADS) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < GF_WARPS; ++ww) sacc += gf_acc[(size_t)ww * CC * n + i];
+    gp[i] = sacc;
   }
 }
 
@@ -370,7 +480,7 @@ __global__ void three_interpolate_kernel(const float* __restrict__ points, const
       __fmaf_rn(p[idx[o + 2]], weight[o + 2], __fmaf_rn(p[idx[o]], weight[o], __fmul_rn(p[idx[o + 1]], weight[o + 1])));
 }
 
-static size_t csr_ws_bytes(int b, int n, int E) { return (size_t)b * ((size_t)n + 1 + (size_t)E) * sizeof(int); }
+static size_t csr_ws_bytes(int b, int n, int E) { return 16 + (size_t)b * ((size_t)n + 1 + (size_t)E) * sizeof(int); }
 
 static int pick_W(int n, int threads) {
   int W = threads / 32;
@@ -379,8 +489,10 @@ static int pick_W(int n, int threads) {
 }
 
 static int run_csr_grad(const float* grad_out, const float* weight, const int32_t* idx, int b, int c, int n, int E,
-                        int e_div, float* grad_points, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                        int e_div, float* grad_points, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                        const int* fast_flag = nullptr) {
   if (workspace_bytes < csr_ws_bytes(b, n, E) || !workspace) return GEOA3_EWORKSPACE;
+  int* csr = (int*)workspace + 4;  // the first 16 bytes hold the dispatch flag
   const int W = pick_W(n, CSRG_THREADS);
   const size_t sm1 = (size_t)W * ((n + 1) & ~1) * 4;
   if (sm1 > 200 * 1024) return GEOA3_EUNSUPPORTED;
@@ -392,7 +504,7 @@ static int run_csr_grad(const float* grad_out, const float* weight, const int32_
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  csr_global_kernel<<<b, CSRG_THREADS, sm1, s>>>(idx, E, n, W, (int*)workspace);
+  csr_global_kernel<<<b, CSRG_THREADS, sm1, s>>>(idx, E, n, W, csr, fast_flag);
   int err = GEOA3_LAUNCH_RESULT();
   if (err) return err;
   const size_t coop_smem = (size_t)E * 4 + (size_t)((n + 1 + 3) & ~3) * 4 + (size_t)E * 2;
@@ -405,7 +517,7 @@ static int run_csr_grad(const float* grad_out, const float* weight, const int32_
       coop_attr = true;
     }
     csr_gather_grad_coop_kernel<<<dim3(ceil_div(c, GG2_CC), b), GG2_THREADS, coop_smem, s>>>(
-        grad_out, (const int*)workspace, c, n, E, grad_points);
+        grad_out, csr, c, n, E, grad_points, fast_flag);
     return GEOA3_LAUNCH_RESULT();
   }
   const int Eg = E / e_div;
@@ -414,9 +526,54 @@ static int run_csr_grad(const float* grad_out, const float* weight, const int32_
     tile = 24 * 1024;  // 96 KB tiles, two CTAs per SM
     if (n > 8 * GG_THREADS) return GEOA3_EUNSUPPORTED;
   }
-  csr_gather_grad_kernel<<<dim3(c, b), GG_THREADS, (size_t)tile * 4, s>>>(grad_out, weight, (const int*)workspace, c, n, E,
-                                                                         e_div, tile, grad_points);
+  csr_gather_grad_kernel<<<dim3(c, b), GG_THREADS, (size_t)tile * 4, s>>>(grad_out, weight, csr, c, n, E, e_div, tile,
+                                                                         grad_points, fast_flag);
   return GEOA3_LAUNCH_RESULT();
+}
+
+template <int CC>
+static int launch_fwd_order(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, int ns,
+                            float* grad_points, const int* flag, cudaStream_t s) {
+  const size_t smem = (size_t)GF_WARPS * CC * n * 4;
+  cudaError_t e = cudaFuncSetAttribute(group_grad_fwd_order_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  group_grad_fwd_order_kernel<CC><<<dim3(ceil_div(c, CC), b), GF_THREADS, smem, s>>>(grad_out, idx, c, n, m, ns,
+                                                                                    grad_points, flag);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+// group_points_grad: forward-order kernel when every index row has the ball-query shape (checked on the device),
+// generic CSR path otherwise; both are launched, each exits immediately when it is not its turn.
+static int run_group_grad(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, int ns,
+                          float* grad_points, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const int E = m * ns;
+  if (workspace_bytes < csr_ws_bytes(b, n, E) || !workspace) return GEOA3_EWORKSPACE;
+  int* flag = (int*)workspace;
+  // channels per CTA: measured best on B200 is 2 (4 KB of private accumulators per warp at n = 512 keeps ~50 warps
+  // resident per SM; 4 or 8 channels amortise the index handling better but starve the SM of warps)
+  int CC = 0;
+  if ((size_t)GF_WARPS * 2 * n * 4 <= 100 * 1024) CC = 2;
+  else if ((size_t)GF_WARPS * n * 4 <= 200 * 1024) CC = 1;
+  if (!CC) return run_csr_grad(grad_out, nullptr, idx, b, c, n, E, 1, grad_points, workspace, workspace_bytes, s);
+  if (c == 1) CC = 1;
+  if (const char* ov = getenv("GEOA3_GF_CC")) {  // tuning knob (tools/time_kernels.py), not part of the API
+    const int v = atoi(ov);
+    if ((v == 1 || v == 2 || v == 4 || v == 8) && (size_t)GF_WARPS * v * n * 4 <= 200 * 1024) CC = v;
+  }
+  cudaError_t e = cudaMemsetAsync(flag, 0, 16, s);
+  if (e != cudaSuccess) return (int)e;
+  fwd_order_ok_kernel<<<ceil_div(b * m, 8), 256, 0, s>>>(idx, b * m, ns, n, flag);
+  int err = GEOA3_LAUNCH_RESULT();
+  if (err) return err;
+  switch (CC) {
+    case 8: err = launch_fwd_order<8>(grad_out, idx, b, c, n, m, ns, grad_points, flag, s); break;
+    case 4: err = launch_fwd_order<4>(grad_out, idx, b, c, n, m, ns, grad_points, flag, s); break;
+    case 2: err = launch_fwd_order<2>(grad_out, idx, b, c, n, m, ns, grad_points, flag, s); break;
+    default: err = launch_fwd_order<1>(grad_out, idx, b, c, n, m, ns, grad_points, flag, s); break;
+  }
+  if (err) return err;
+  return run_csr_grad(grad_out, nullptr, idx, b, c, n, E, 1, grad_points, workspace, workspace_bytes, s, flag);
 }
 
 }  // namespace geoa3
@@ -498,8 +655,8 @@ extern "C" int geoa3_group_points_grad(const float* grad_out, const int32_t* idx
                                        geoa3_stream_t stream) {
   GEOA3_CHECK_ARG(grad_out && idx && grad_points && b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0);
   if (b > 65535 || c > 65535) return GEOA3_EUNSUPPORTED;
-  return run_csr_grad(grad_out, nullptr, idx, b, c, n, npoints * nsample, 1, grad_points, workspace, workspace_bytes,
-                      (cudaStream_t)stream);
+  return run_group_grad(grad_out, idx, b, c, n, npoints, nsample, grad_points, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
 }
 
 extern "C" int geoa3_gather_points(const float* points, const int32_t* idx, int b, int c, int n, int m, float* out,

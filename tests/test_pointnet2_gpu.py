@@ -142,6 +142,35 @@ def test_group_points_and_grad(b, c, n, m, ns):
         assert rel_err(f.grad.cpu().numpy(), ext.group_points_grad(cu(go), cu(idx), n).cpu().numpy()) < 1e-5
 
 
+def test_group_grad_arbitrary_idx_takes_generic_path():
+    """Index rows that do NOT have the ball-query shape (random, with repeats anywhere): the device-side shape
+    check must route the call to the generic CSR path; results still match the oracle and stay deterministic."""
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(3)
+    for (b, c, n, m, ns) in ((3, 16, 300, 40, 24), (2, 5, 128, 64, 32)):
+        idx = rng.integers(0, n, (b, m, ns)).astype(np.int32)
+        idx[:, ::3, 5:9] = idx[:, ::3, 1:2]  # repeats in the middle of a row
+        feats = rng.standard_normal((b, c, n)).astype(np.float32)
+        go = rng.standard_normal((b, c, m, ns)).astype(np.float32)
+        grads = []
+        for _ in range(2):
+            f = cu(feats).requires_grad_(True)
+            pu.grouping_operation(f, cu(idx)).backward(cu(go))
+            grads.append(f.grad.clone())
+        assert rel_err(grads[0].cpu().numpy(), O.group_points_grad(go, idx, n)) < 1e-5
+        assert torch.equal(grads[0], grads[1])
+        # one bad row among ball-query rows also forces the generic path
+        xyz = clouds(b, n, 2)
+        new = np.stack([xyz[i, O.fps(xyz[i:i + 1], m)[0]] for i in range(b)])
+        idx2 = O.ball_query(new, xyz, 0.3, ns)
+        idx2[0, 0, 1] = idx2[0, 0, 0]
+        idx2[0, 0, 2] = (idx2[0, 0, 0] + 1) % n
+        f = cu(feats).requires_grad_(True)
+        pu.grouping_operation(f, cu(idx2)).backward(cu(go))
+        assert rel_err(f.grad.cpu().numpy(), O.group_points_grad(go, idx2, n)) < 1e-5
+
+
 def test_gather_and_grad():
     from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
 
