@@ -95,6 +95,87 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits
   }
 }
 
+// Single-warp variant for n <= 1024: a whole cloud lives in the registers of ONE warp (P points per lane, packed
+// two per register pair), so a round needs no block barrier and no shared-memory exchange at all.  A round is
+// issue-bound on that one warp (IPC ~0.55), so the loop is cut to ~5 instructions per point: packed distance
+// (FADD2/FMUL2/FFMA2, pointnet2 contraction order), one FMNMX per point for the running minimum, FMNMX3 trees for
+// per-group maxima, and the tie-break keys are only inspected inside the group(s) that attain the warp-wide
+// maximum (found with one REDUX).  Frozen / padding points keep temp = 0 and key 0, so they need no select.
+template <int P>
+__global__ void __launch_bounds__(32)
+fps_warp_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs) {
+  static_assert(P % 8 == 0, "groups of 8 points");
+  extern __shared__ __align__(16) float s_xyz[];  // [3][n] SoA mirror (broadcast of the last pick)
+  const int cloud = blockIdx.x, lane = threadIdx.x;
+  const float* p = xyz + (size_t)cloud * n * 3;
+  int32_t* out = idxs + (size_t)cloud * m;
+  constexpr int H = P / 2, G = P / 8;
+  float2 px[H], py[H], pz[H], temp[H];
+  unsigned tk[P];
+  {
+    float lx[P], ly[P], lz[P];
+#pragma unroll
+    for (int t = 0; t < P; ++t) {  // all loads first (independent), then the per-point setup
+      const int k = lane + t * 32;
+      const bool ok = k < n;
+      lx[t] = ok ? p[k * 3] : 0.f; ly[t] = ok ? p[k * 3 + 1] : 0.f; lz[t] = ok ? p[k * 3 + 2] : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < P; ++t) {
+      const int k = lane + t * 32;
+      tk[t] = 0u;
+      float t0 = 0.f;
+      if (k < n) {
+        s_xyz[k] = lx[t]; s_xyz[n + k] = ly[t]; s_xyz[2 * n + k] = lz[t];
+        const float mag = __fmaf_rn(lz[t], lz[t], __fmaf_rn(lx[t], lx[t], __fmul_rn(ly[t], ly[t])));
+        const unsigned rtid = ref_bits ? (__brev((unsigned)(k % ref_bs)) >> (32 - ref_bits)) : 0u;
+        if (!((double)mag <= 1e-3)) { tk[t] = ~((rtid << 20) | (unsigned)k); t0 = 1e10f; }
+      }
+      if (t & 1) { px[t >> 1].y = lx[t]; py[t >> 1].y = ly[t]; pz[t >> 1].y = lz[t]; temp[t >> 1].y = t0; }
+      else { px[t >> 1].x = lx[t]; py[t >> 1].x = ly[t]; pz[t >> 1].x = lz[t]; temp[t >> 1].x = t0; }
+    }
+  }
+  if (lane == 0) out[0] = 0;
+  __syncwarp();
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = -s_xyz[old], y1 = -s_xyz[n + old], z1 = -s_xyz[2 * n + old];
+    const float2 nx = make_float2(x1, x1), ny = make_float2(y1, y1), nz = make_float2(z1, z1);
+    float hg[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float mx = 0.f;
+#pragma unroll
+      for (int h = g * 4; h < g * 4 + 4; ++h) {
+        const float2 d = dist2x2_pn2(px[h], py[h], pz[h], nx, ny, nz);
+        temp[h].x = fminf(d.x, temp[h].x);  // frozen / padding points sit at 0 forever
+        temp[h].y = fminf(d.y, temp[h].y);
+        mx = fmaxf(mx, fmaxf(temp[h].x, temp[h].y));
+      }
+      hg[g] = mx;
+    }
+    float hmax = hg[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) hmax = fmaxf(hmax, hg[g]);
+    const float gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hmax)));  // >= +0: bit order
+    unsigned bl = 0u;
+    if (hmax == gmax) {  // only the lane(s) holding the maximum look at their tie-break keys
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (hg[g] == gmax) {
+#pragma unroll
+          for (int h = g * 4; h < g * 4 + 4; ++h) {
+            bl = max(bl, temp[h].x == gmax ? tk[2 * h] : 0u);
+            bl = max(bl, temp[h].y == gmax ? tk[2 * h + 1] : 0u);
+          }
+        }
+    }
+    const unsigned lo = __reduce_max_sync(0xffffffffu, bl);
+    old = lo != 0u ? (int)((~lo) & 0xFFFFFu) : 0;
+    if (lane == 0) out[j] = old;
+  }
+}
+
 // ============================================================================ ball query
 constexpr int BQ_WARPS = 8;
 constexpr int BQ_PER_WARP = 8;  // centroids handled sequentially by one warp
@@ -597,7 +678,11 @@ extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  if (n <= 4096) {
+  if (n <= 512) {
+    fps_warp_kernel<16><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 1024) {
+    fps_warp_kernel<32><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 4096) {
     const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
     fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx);
   } else if (n <= 8192) {
