@@ -3,28 +3,39 @@
 // Thread-per-query brute force, candidates streamed through shared memory as SoA float4 broadcasts
 // and evaluated two at a time on the packed fp32 pipe (pinned fma-chain arithmetic, see common.cuh).
 // Each thread keeps its K best (dist, idx) pairs sorted in registers; tau = current K-th distance.
-// A candidate passes only if d < tau (strict; candidates are visited in ascending index, so among
-// equal distances the lowest indices survive => lexicographic (dist, idx) order, the pinned rule).
-// Passing candidates are NOT inserted on the spot (that would serialise the warp on its slowest
-// lane every step): they are appended to a small per-thread queue in shared memory and the warp
-// drains all queues together — a branch-free sorted-insert network executed by all 32 lanes — when
-// any lane's queue is nearly full.  The queue preserves arrival order, so ties keep their order.
+// The result is the K lexicographically smallest (dist, ORIGINAL index) pairs, ascending — the pinned rule.
 //
-// Hinted threshold.  Scanning in index order from tau = +inf inserts ~K*ln(N/K) candidates per query, and the
-// insert network (5 alu ops per list slot) is what the half-width alu pipe chokes on.  If the caller passes,
-// per query, a list of candidate indices (typically the neighbours found one optimisation step earlier),
-// tau starts at the largest exact distance to those candidates — an upper bound of the true K-th distance
-// whenever the list (plus the query's own index) holds K distinct points — so only ~K candidates are ever
-// inserted.  The bound is self-verifying: if fewer than K candidates passed it the CTA rescans with
-// tau = +inf.  Any hint therefore yields the exact lexicographic top-K; a bad one only costs time.
+// One alu op per candidate.  The alu pipe (compares, selects, integer adds) is half as wide as the fma pipe,
+// so the per-candidate bookkeeping is reduced to a funnel shift: s = d - next(tau) is formed on the fma pipe
+// (its sign is exact) and the sign bit is shifted into a 32-candidate pass mask.  Set bits are expanded into a
+// per-thread index queue in shared memory once per 32 candidates; passing candidates are NOT inserted on the
+// spot (that would serialise the warp on its slowest lane): the warp drains all queues together through a
+// branch-free sorted-insert network when any lane's queue is nearly full.  The exact distance is recomputed at
+// drain time and the network orders by (dist, original index), so the visiting order is irrelevant.
+//
+// Hinted threshold.  Scanning from tau = +inf inserts ~K*ln(N/K) candidates per query, and the insert network
+// is what the alu pipe chokes on.  If the caller passes, per query, a list of candidate indices (typically
+// the neighbours found one optimisation step earlier), tau starts at the largest exact distance to those
+// candidates and to the query's own index — an upper bound of the true K-th distance whenever these are K
+// distinct points — so only ~K candidates are ever inserted.  The bound is self-verifying: if fewer than K
+// candidates passed it the CTA rescans with tau = +inf.  Any hint yields the exact top-K.
+//
+// Spatial pruning.  The caller may pass the clouds ALREADY ARRANGED in a visiting order (position t holds original
+// point perm[t], e.g. the Morton order of the original cloud computed once per attack; staging stays coalesced):
+// a warp's 32 queries and every group of 32 staged candidates are then spatially compact, each group carries its
+// bounding box, and a warp skips the group when no lane's box distance can reach its tau.  Indices are reported
+// in original numbering (through perm); any permutation is valid.
+#include <climits>
+
 #include "common.cuh"
 
 namespace geoa3 {
 
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_CHUNK = 1024;  // candidates per shared-memory pass (12 KB; static smem stays under 48 KB)
+constexpr int KNN_CHUNK = 1024;  // candidates per shared-memory pass (static smem stays under 48 KB)
 constexpr int KNN_QDEPTH = 56;   // queue slots per thread (indices only; distances are recomputed at drain):
                                  // drained when > 24 are pending, and one 32-candidate group adds at most 32
+constexpr float KNN_INF = __builtin_huge_valf();
 
 template <int K>
 struct TopK {
@@ -32,15 +43,18 @@ struct TopK {
   int i[K];
   __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int l = 0; l < K; ++l) { d[l] = __int_as_float(0x7f800000); i[l] = -1; }
+    for (int l = 0; l < K; ++l) { d[l] = KNN_INF; i[l] = -1; }
   }
-  // sorted insert of (x, xi); elements equal to x stay in front of it (arrival order = index order)
+  // sorted insert of (x, xi); a no-op feed is (+inf, INT_MAX).  LEX: order by (distance, index) — needed when
+  // candidates arrive in a permuted order; otherwise arrival order IS index order and "equal stays in front"
+  // gives the same lexicographic result with 3 fewer alu ops per slot.
+  template <bool LEX>
   __device__ __forceinline__ void insert(float x, int xi) {
     float cd = x;
     int ci = xi;
 #pragma unroll
     for (int l = 0; l < K; ++l) {
-      const bool p = x < d[l];
+      const bool p = LEX ? (x < d[l] || (x == d[l] && xi < i[l])) : (x < d[l]);
       const float od = d[l];
       const int oi = i[l];
       d[l] = p ? cd : od;
@@ -52,36 +66,42 @@ struct TopK {
   __device__ __forceinline__ float tau() const { return d[K - 1]; }
 };
 
-template <int K>
+template <int K, bool PRUNE>
 __global__ void __launch_bounds__(KNN_THREADS, K <= 17 ? 6 : 4)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n, int m, int kout, int drop,
+           const int32_t* __restrict__ perm_q, const int32_t* __restrict__ perm_c, const int32_t* __restrict__ iperm_c,
            const int32_t* hint, int hint_k, int32_t* idx_out, float* __restrict__ dist_out) {
   __shared__ __align__(16) float sx[KNN_CHUNK];
   __shared__ __align__(16) float sy[KNN_CHUNK];
   __shared__ __align__(16) float sz[KNN_CHUNK];
+  __shared__ int so[PRUNE ? KNN_CHUNK : 1];             // original index of the staged candidate
+  __shared__ float sbb[PRUNE ? KNN_CHUNK / 32 : 1][6];  // bounding box of every 32-candidate group
   __shared__ int qj[KNN_QDEPTH][KNN_THREADS];
 
   const int cloud = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int qi = blockIdx.x * KNN_THREADS + tid;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int slot = blockIdx.x * KNN_THREADS + tid;  // position in visiting order
   const float* qbase = query + (size_t)cloud * 3 * n;
   const float* cbase = ref + (size_t)cloud * 3 * m;
-  const int qq = min(qi, n - 1);
-  const float qx = qbase[qq], qy = qbase[n + qq], qz = qbase[2 * n + qq];
+  const int32_t* pc = perm_c ? perm_c + (size_t)cloud * m : nullptr;
+  const int32_t* ipc = iperm_c ? iperm_c + (size_t)cloud * m : nullptr;
+  const int sl = min(slot, n - 1);
+  const int qq = perm_q ? perm_q[(size_t)cloud * n + sl] : sl;  // ORIGINAL index of this thread's query
+  const bool live = slot < n;
+  const int qpos = perm_q ? sl : qq;  // the query cloud is stored by position when perm_q is given
+  const float qx = qbase[qpos], qy = qbase[n + qpos], qz = qbase[2 * n + qpos];
   const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
 
   // hinted start threshold (evaluated below, once the first candidate chunk sits in shared memory)
-  float tau0 = __int_as_float(0x7f800000);
-  const bool use_hint = hint != nullptr && hint_k + 1 >= K;
+  float tau0 = KNN_INF;
+  const bool use_hint = hint != nullptr && hint_k + 1 >= K && (!pc || ipc);
 
   TopK<K> top;
   bool rescan = false;
   do {
   top.init();
-  float tau = tau0;
+  float tau = tau0;  // candidates with d <= tau are worth an exact look
   bool hint_pending = use_hint && !rescan;
-  // per-thread queue of passing candidate indices: qp walks down column `tid` of qj; the hot loop only
-  // does "compare, predicated store, predicated pointer bump" per candidate
   // 32-bit shared-window address of this thread's queue column, kept in ONE register: the compiler otherwise
   // re-materialises the base (3 extra predicated instructions per candidate)
   const unsigned q0 = (unsigned)__cvta_generic_to_shared(&qj[0][tid]);
@@ -93,15 +113,16 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
     const int cnt = (int)((qa - q0) / QSTRIDE);
     const int mx = __reduce_max_sync(0xffffffffu, cnt);
     for (int r = 0; r < mx; ++r) {
-      // lanes without an r-th entry feed +inf, which the network leaves in the carry
-      float x = __int_as_float(0x7f800000);
-      int xi = -1;
+      // lanes without an r-th entry feed (+inf, INT_MAX), which the network leaves in the carry
+      float x = KNN_INF;
+      int xi = INT_MAX;
       if (r < cnt) {
-        xi = qj[r][tid];
-        const int l = xi - c0;  // the queue is drained before the staged chunk is replaced
-        x = dist2(sx[l], sy[l], sz[l], qx, qy, qz);  // bit-identical to the packed evaluation
+        const int l = qj[r][tid];  // position inside the staged chunk (drained before the chunk is replaced)
+        x = dist2(sx[l], sy[l], sz[l], qx, qy, qz);  // the pinned arithmetic decides
+        xi = PRUNE ? so[l] : c0 + l;
+        if (!(x <= tau0)) { x = KNN_INF; xi = INT_MAX; }  // outside the hinted bound: must not count as a pass
       }
-      top.insert(x, xi);
+      top.template insert<PRUNE>(x, xi);
     }
     qa = q0;
     tau = fminf(tau0, top.tau());
@@ -111,36 +132,59 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
     const int cn = min(KNN_CHUNK, m - c0);
     const int cn32 = (cn + 31) & ~31;
     __syncthreads();
-    for (int t = tid; t < cn32; t += KNN_THREADS) {
+    for (int t = tid; t < cn32; t += KNN_THREADS) {  // a warp stages 32 consecutive positions = one group
       const bool ok = t < cn;
-      sx[t] = ok ? cbase[c0 + t] : __int_as_float(0x7f800000);  // +inf padding: d = +inf never passes
+      const int o = ok ? (pc ? pc[c0 + t] : c0 + t) : 0;
+      sx[t] = ok ? cbase[c0 + t] : KNN_INF;  // +inf padding: d = +inf never passes (ref is stored by position)
       sy[t] = ok ? cbase[m + c0 + t] : 0.f;
       sz[t] = ok ? cbase[2 * m + c0 + t] : 0.f;
+      if (PRUNE) {
+        so[t] = o;
+        float lx = ok ? sx[t] : 3e38f, ly = ok ? sy[t] : 3e38f, lz = ok ? sz[t] : 3e38f;
+        float hx = ok ? sx[t] : -3e38f, hy = ok ? sy[t] : -3e38f, hz = ok ? sz[t] : -3e38f;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, s)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, s));
+          ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, s)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, s));
+          lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, s)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, s));
+        }
+        if (lane == 0) {
+          float* bb = sbb[t >> 5];
+          bb[0] = lx; bb[1] = ly; bb[2] = lz; bb[3] = hx; bb[4] = hy; bb[5] = hz;
+        }
+      }
     }
     __syncthreads();
     if (hint_pending) {
-      // tau0 = max exact distance to the hinted candidates and to the point of the same index (the self match
-      // of a self-query), nudged one ulp up so that the strict test admits equality.  Candidates of the staged
-      // chunk are read from shared memory, the rest (m > KNN_CHUNK only) from global memory.
+      // tau0 = max exact distance to the hinted candidates and to the point with the query's own index (the
+      // self match of a self-query).  Candidates of the staged chunk are read from shared memory (through the
+      // inverse permutation when there is one), the rest from global memory.
       hint_pending = false;
       const int32_t* h = hint + ((size_t)cloud * n + qq) * hint_k;  // may alias idx_out: own row, read before write
       auto cand_d = [&](int j) {
         j = min(max(j, 0), m - 1);
-        return j < cn ? dist2(sx[j], sy[j], sz[j], qx, qy, qz)
-                      : dist2(cbase[j], cbase[m + j], cbase[2 * m + j], qx, qy, qz);
+        const int pos = pc ? ipc[j] : j;  // position of original index j (hints need iperm_c when permuted)
+        return pos < cn ? dist2(sx[pos], sy[pos], sz[pos], qx, qy, qz)
+                        : dist2(cbase[pos], cbase[m + pos], cbase[2 * m + pos], qx, qy, qz);
       };
       float mx = cand_d(qq);
       for (int t = 0; t < hint_k; ++t) mx = fmaxf(mx, cand_d(h[t]));
-      if (mx < 3.0e38f) tau0 = __uint_as_float(__float_as_uint(mx) + 1u);
+      if (mx < 3.0e38f) tau0 = mx;
       tau = tau0;
     }
-    // The alu pipe (compares, selects, integer adds) is half as wide as the fma pipe, so the per-candidate
-    // bookkeeping is reduced to ONE alu op: s = d - tau is formed on the fma pipe (its sign is exact) and a
-    // funnel shift pushes the sign bit into a 32-candidate pass mask.  Set bits are expanded into the index
-    // queue once per 32 candidates (a short divergent loop, ~2% of the candidates pass).
     for (int j = 0; j < cn32; j += 32) {
+      if (PRUNE) {  // can any candidate of this group be within tau of any query of this warp?
+        const float* bb = sbb[j >> 5];
+        const float ex = fmaxf(fmaxf(bb[0] - qx, qx - bb[3]), 0.f);
+        const float ey = fmaxf(fmaxf(bb[1] - qy, qy - bb[4]), 0.f);
+        const float ez = fmaxf(fmaxf(bb[2] - qz, qz - bb[5]), 0.f);
+        const float lb = ex * ex + ey * ey + ez * ez;  // d_pin >= lb*(1-1e-6) for every candidate in the box
+        if (!__any_sync(0xffffffffu, live && lb * 0.9999f <= tau)) continue;
+      }
       unsigned mask = 0u;
-      const float2 ntau = make_float2(-tau, -tau);
+      // pass <=> d <= tau <=> d - next(tau) < 0 (sign bit); next(+inf) stays +inf, +inf padding gives +inf / NaN(+)
+      const float taun = tau < 3.0e38f ? __uint_as_float(__float_as_uint(tau) + 1u) : KNN_INF;
+      const float2 ntau = make_float2(-taun, -taun);
 #pragma unroll 2
       for (int u = 0; u < 32; u += 8) {
         const float4 cxa = *reinterpret_cast<const float4*>(sx + j + u), cxb = *reinterpret_cast<const float4*>(sx + j + u + 4);
@@ -150,7 +194,6 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
         const float2 s23 = __fadd2_rn(dist2x2(make_float2(cxa.z, cxa.w), make_float2(cya.z, cya.w), make_float2(cza.z, cza.w), nqx, nqy, nqz), ntau);
         const float2 s45 = __fadd2_rn(dist2x2(make_float2(cxb.x, cxb.y), make_float2(cyb.x, cyb.y), make_float2(czb.x, czb.y), nqx, nqy, nqz), ntau);
         const float2 s67 = __fadd2_rn(dist2x2(make_float2(cxb.z, cxb.w), make_float2(cyb.z, cyb.w), make_float2(czb.z, czb.w), nqx, nqy, nqz), ntau);
-        // d < tau  <=>  sign(d - tau) set  (d = +inf padding gives +inf or the positive canonical NaN)
         mask = __funnelshift_l(__float_as_uint(s01.x), mask, 1);
         mask = __funnelshift_l(__float_as_uint(s01.y), mask, 1);
         mask = __funnelshift_l(__float_as_uint(s23.x), mask, 1);
@@ -160,11 +203,10 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
         mask = __funnelshift_l(__float_as_uint(s67.x), mask, 1);
         mask = __funnelshift_l(__float_as_uint(s67.y), mask, 1);
       }
-      const int jj = c0 + j;
-      while (mask) {  // bit 31 is candidate jj, bit 0 is candidate jj+31: ascending index = descending bit
+      while (mask) {  // bit 31 is position j, bit 0 is position j+31: ascending position = descending bit
         const int t = __clz(mask);
         mask &= ~(0x80000000u >> t);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(jj + t) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(j + t) : "memory");
         qa += QSTRIDE;
       }
       if (__any_sync(0xffffffffu, qa > q0 + (KNN_QDEPTH - 32) * QSTRIDE)) drain();
@@ -172,13 +214,13 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
     drain();  // queue entries index the staged chunk: empty it before the chunk is replaced
   }
   // fewer than K candidates under the hinted bound => the bound was not valid for this query: redo unhinted
-  rescan = __syncthreads_or((qi < n) && top.i[K - 1] < 0 && tau0 != __int_as_float(0x7f800000));
-  tau0 = __int_as_float(0x7f800000);
+  rescan = __syncthreads_or(live && top.i[K - 1] < 0 && tau0 != KNN_INF);
+  tau0 = KNN_INF;
   } while (rescan);
 
-  if (qi < n) {
-    int32_t* io = idx_out + ((size_t)cloud * n + qi) * kout;
-    float* dn = dist_out ? dist_out + ((size_t)cloud * n + qi) * kout : nullptr;
+  if (live) {
+    int32_t* io = idx_out + ((size_t)cloud * n + qq) * kout;
+    float* dn = dist_out ? dist_out + ((size_t)cloud * n + qq) * kout : nullptr;
 #pragma unroll
     for (int l = 0; l < K; ++l) {
       const int o = l - drop;
@@ -192,16 +234,23 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
 
 template <int K>
 static int launch_knn(const float* query, const float* ref, int b, int n, int m, int kout, int drop,
-                      const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
+                      const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const int32_t* hint,
+                      int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
   dim3 grid(ceil_div(n, KNN_THREADS), b, 1);
-  knn_kernel<K><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, hint, hint_k, idx, dist);
+  if (perm_c)
+    knn_kernel<K, true><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, perm_q, perm_c, iperm_c, hint, hint_k,
+                                                     idx, dist);
+  else
+    knn_kernel<K, false><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, perm_q, nullptr, nullptr, hint,
+                                                      hint_k, idx, dist);
   return GEOA3_LAUNCH_RESULT();
 }
 
 }  // namespace geoa3
 
 extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int m, int K, int drop,
-                         const int32_t* hint, int hint_k, int32_t* idx, float* dist, geoa3_stream_t stream) {
+                         const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const int32_t* hint,
+                         int hint_k, int32_t* idx, float* dist, geoa3_stream_t stream) {
   using namespace geoa3;
   GEOA3_CHECK_ARG(query && ref && idx);
   GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
@@ -211,9 +260,11 @@ extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int
   const int kout = K - drop;
   // the list size is a compile-time constant (register arrays); a larger list than requested is still
   // exact: the first K entries of the top-K' (K' >= K) are the top-K.
-  if (K <= 3) return launch_knn<3>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
-  if (K <= 5) return launch_knn<5>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
-  if (K <= 9) return launch_knn<9>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
-  if (K <= 17) return launch_knn<17>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
-  return launch_knn<33>(query, ref, b, n, m, kout, drop, hint, hint_k, idx, dist, s);
+#define GEOA3_KNN_ARGS query, ref, b, n, m, kout, drop, perm_q, perm_c, iperm_c, hint, hint_k, idx, dist, s
+  if (K <= 3) return launch_knn<3>(GEOA3_KNN_ARGS);
+  if (K <= 5) return launch_knn<5>(GEOA3_KNN_ARGS);
+  if (K <= 9) return launch_knn<9>(GEOA3_KNN_ARGS);
+  if (K <= 17) return launch_knn<17>(GEOA3_KNN_ARGS);
+  return launch_knn<33>(GEOA3_KNN_ARGS);
+#undef GEOA3_KNN_ARGS
 }

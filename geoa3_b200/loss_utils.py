@@ -41,9 +41,17 @@ class HintBuffers(object):
     the previous step's indices are such a seed.  The kernels read the hint and write the new result into
     the SAME buffer, so the hints stay fresh even when the whole step is replayed as a CUDA graph."""
 
-    def __init__(self):
+    def __init__(self, prune_min_n_knn=2048):
         self.d1 = self.jstar = self.d2 = self.istar = None
         self.nbr = {}
+        # visiting order for the pruned searches: Morton order of the ORIGINAL cloud, computed once (first call)
+        self.perm = self.iperm = self.ori_arranged = None
+        self.prune_min_n_knn = prune_min_n_knn  # measured: box pruning of the kNN scan only pays for larger clouds
+
+    def ensure_order(self, ori):
+        if self.perm is None or self.perm.shape != (ori.shape[0], ori.shape[2]):
+            self.perm, self.iperm = ops.morton_order(ori)
+            self.ori_arranged = ops.arrange(ori, self.perm)
 
     def ensure_nn(self, b, n, m, dev):
         if self.jstar is None or self.jstar.shape != (b, n) or self.istar.shape != (b, m):
@@ -111,7 +119,14 @@ def _nn(e, both):
         hb = e.hints
         if hb is not None:  # persistent buffers: hint and result alias, refreshed in place
             hb.ensure_nn(b, n, m, e.adv_c.device)
-            ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, out=(hb.d1, hb.jstar, hb.d2, hb.istar))
+            if n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
+                hb.ensure_order(e.ori_c)
+                ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, perm_a=hb.perm, perm_o=hb.perm,
+                            iperm_a=hb.iperm, iperm_o=hb.iperm, ori_arranged=hb.ori_arranged,
+                            out=(hb.d1, hb.jstar, hb.d2, hb.istar))
+            else:
+                ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar,
+                            out=(hb.d1, hb.jstar, hb.d2, hb.istar))
             e.d1, e.jstar, e.d2, e.istar = hb.d1, hb.jstar, hb.d2, hb.istar
         else:
             key = (e.adv_c.device, b, n, m)
@@ -141,6 +156,9 @@ def _nbr(e, k):
             buf = hb.nbr.get(k)
             if buf is None or buf.shape[:2] != e.adv_c.shape[::2]:
                 hb.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1)[0]  # first call: nothing to hint with
+            elif hb.perm is not None and e.adv_c.shape[2] >= hb.prune_min_n_knn and e.adv_c.shape[2] == hb.perm.shape[1]:
+                ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, perm_q=hb.perm, perm_c=hb.perm,
+                        iperm_c=hb.iperm)
             else:
                 ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf)
             e.nbr[k] = hb.nbr[k]

@@ -19,7 +19,37 @@ def _guard(t):
     return torch.cuda.device(t.device)
 
 
-def nn_pair(adv, ori, both=True, hint_a2o=None, hint_o2a=None, out=None):
+def morton_order(pc, bits=10):
+    """pc [b,3,n] -> (perm [b,n] int32, iperm [b,n] int32): points sorted by the Morton code of their coordinates
+    quantised to `bits` bits per axis over the cloud's bounding box.  Plain torch ops — computed ONCE per attack
+    on the original cloud, not on the per-step path.  Any permutation is valid for the kernels; this one makes
+    groups of 32 consecutive points spatially compact so that bounding-box pruning bites."""
+    with torch.no_grad():
+        lo = pc.amin(2, keepdim=True)
+        ext = (pc.amax(2, keepdim=True) - lo).amax(1, keepdim=True).clamp_min(1e-20)
+        q = ((pc - lo) / ext * (2 ** bits - 1)).round().clamp_(0, 2 ** bits - 1).to(torch.int64)
+
+        def spread(v):  # insert two zero bits between the bits of a 10-bit value
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+
+        code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+        perm = torch.sort(code, dim=1, stable=True)[1]
+        iperm = torch.empty_like(perm)
+        iperm.scatter_(1, perm, torch.arange(pc.shape[2], device=pc.device).expand_as(perm))
+        return perm.to(torch.int32).contiguous(), iperm.to(torch.int32).contiguous()
+
+
+def arrange(pc, perm):
+    """pc [b,c,n], perm [b,n] int32 -> pc with position t holding original point perm[t] (one gather kernel)."""
+    return torch.gather(pc, 2, perm.long()[:, None, :].expand(-1, pc.shape[1], -1)).contiguous()
+
+
+def nn_pair(adv, ori, both=True, hint_a2o=None, hint_o2a=None, out=None, perm_a=None, perm_o=None, iperm_a=None,
+            iperm_o=None, ori_arranged=None):
     """adv [b,3,n], ori [b,3,m] -> d_a2o [b,n], jstar [b,n] i32, d_o2a [b,m] | None, istar [b,m] | None.
     hint_* (int32, optional) seed the search (exact for any seed); `out` = (d1, j1, d2, i2) preallocated
     buffers (j1/i2 may be the hint tensors themselves: in-place refresh of persistent hints)."""
@@ -35,17 +65,23 @@ def nn_pair(adv, ori, both=True, hint_a2o=None, hint_o2a=None, out=None):
         j1 = torch.empty(b, n, device=adv.device, dtype=torch.int32)
         d2 = torch.empty(b, m, device=adv.device, dtype=torch.float32) if both else None
         i2 = torch.empty(b, m, device=adv.device, dtype=torch.int32) if both else None
-    for h in (hint_a2o, hint_o2a):
+    for h in (hint_a2o, hint_o2a, perm_a, perm_o, iperm_a, iperm_o):
         if h is not None:
-            require_cuda_i32(h, "hint")
+            require_cuda_i32(h, "hint / perm")
+    if (perm_a is None) != (perm_o is None):
+        raise RuntimeError("perm_a and perm_o come together")
+    if perm_a is not None:  # the kernel wants both clouds arranged in visiting order (coalesced staging)
+        adv = arrange(adv, perm_a)
+        ori = ori_arranged if ori_arranged is not None else arrange(ori, perm_o)
     with _guard(adv):
         _count(1)
-        check(_lib.load().geoa3_nn_pair(ptr(adv), ptr(ori), b, n, m, ptr(hint_a2o), ptr(hint_o2a) if both else None,
-                                        ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(adv)))
+        check(_lib.load().geoa3_nn_pair(ptr(adv), ptr(ori), b, n, m, ptr(perm_a), ptr(perm_o), ptr(iperm_a),
+                                        ptr(iperm_o), ptr(hint_a2o), ptr(hint_o2a) if both else None, ptr(d1),
+                                        ptr(j1), ptr(d2), ptr(i2), stream(adv)))
     return d1, j1, d2, i2
 
 
-def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None):
+def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=None, perm_c=None, iperm_c=None):
     """query [b,3,n], ref [b,3,m] -> idx [b,n,K-drop] i32 (ascending (dist,idx)), dist | None.
     hint [b,n,hk] int32 (optional) only tightens the start threshold (exact for any hint); `out` may be the
     hint tensor itself (in-place refresh)."""
@@ -53,6 +89,12 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None):
     b, _, n = query.shape
     m = ref.shape[2]
     idx = out if out is not None else torch.empty(b, n, K - drop, device=query.device, dtype=torch.int32)
+    if perm_c is not None:  # arrange the clouds in visiting order (coalesced staging in the kernel)
+        same = query is ref and perm_q is perm_c
+        ref = arrange(ref, perm_c)
+        query = ref if same else (arrange(query, perm_q) if perm_q is not None else query)
+    elif perm_q is not None:
+        query = arrange(query, perm_q)
     hk = 0
     if hint is not None:
         require_cuda_i32(hint, "hint")
@@ -60,8 +102,8 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None):
     dist = torch.empty(b, n, K - drop, device=query.device, dtype=torch.float32) if return_dist else None
     with _guard(query):
         _count(1)
-        check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(hint), hk, ptr(idx), ptr(dist),
-                                    stream(query)))
+        check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(perm_q), ptr(perm_c), ptr(iperm_c),
+                                    ptr(hint), hk, ptr(idx), ptr(dist), stream(query)))
     return idx, dist
 
 

@@ -58,20 +58,31 @@ GEOA3_API const char *geoa3_error_string(int code);
  * hint_a2o [b][n] / hint_o2a [b][m] (nullable) seed each query with a candidate index (default: its own
  * index); results are exact for any seed, a good one (e.g. last step's argmin) makes the search ~2x faster.
  * A hint may alias the corresponding output (in-place update of a persistent buffer).
+ * perm_a [b][n] / perm_o [b][m] (both or none): the clouds are passed ALREADY ARRANGED in a visiting order —
+ * position t of adv holds original point perm_a[t] (likewise ori/perm_o), e.g. the Morton order of the original
+ * cloud computed once per attack.  With a spatially coherent order whole groups of 32 candidates are skipped by
+ * a bounding-box test.  Outputs and hints use ORIGINAL numbering (d_a2o[i], jstar[i] belong to original adv point
+ * i), ties resolve on original indices: results are identical for ANY permutation.  iperm_* (inverse
+ * permutations, nullable) are only needed to honour hints; without them the seed is the same-position point.
  * Replaces: knn_points(adv, ori, K=1) + knn_points(ori, adv, K=1), Lib/loss_utils.py:32-33,41,48,70,92;
  *           Attacker/geoA3_attack.py:65,80. */
-GEOA3_API int geoa3_nn_pair(const float *adv, const float *ori, int b, int n, int m, const int32_t *hint_a2o,
-                            const int32_t *hint_o2a, float *d_a2o, int32_t *jstar, float *d_o2a, int32_t *istar,
-                            geoa3_stream_t stream);
+GEOA3_API int geoa3_nn_pair(const float *adv, const float *ori, int b, int n, int m, const int32_t *perm_a,
+                            const int32_t *perm_o, const int32_t *iperm_a, const int32_t *iperm_o,
+                            const int32_t *hint_a2o, const int32_t *hint_o2a, float *d_a2o, int32_t *jstar,
+                            float *d_o2a, int32_t *istar, geoa3_stream_t stream);
 
 /* K nearest of every query [b][3][n] among ref [b][3][m], ascending (dist, idx); the first `drop`
  * columns are discarded (drop=1 removes the self match exactly like "[:,:,:,1:]").
  * idx [b][n][K-drop] int32, dist (nullable) [b][n][K-drop].  K <= GEOA3_KNN_MAX_K, K <= m.
  * hint [b][n][hint_k] (nullable): candidate indices per query used only to start the selection threshold
  * (self-verifying, results are exact for any hint); may alias idx when hint_k == K-drop.
+ * perm_q [b][n] / perm_c [b][m] (nullable): query / ref are passed already arranged in a visiting order (see
+ * geoa3_nn_pair); iperm_c [b][m] = inverse of perm_c (needed to use hints with a permuted ref).  Results are in
+ * original numbering and identical for any permutation; a spatially coherent one enables bounding-box pruning.
  * Replaces: knn_points(pc, pc, K=k+1).idx[..., 1:], Lib/loss_utils.py:57-58,77-78,139,174. */
 GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int m, int K, int drop,
-                        const int32_t *hint, int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
+                        const int32_t *perm_q, const int32_t *perm_c, const int32_t *iperm_c, const int32_t *hint,
+                        int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
 
 /* Local curvature + per-cloud loss reductions, one CTA per cloud, fixed-order reductions.
  *   kappa_i = (1/k) sum_m |<nrm_i, v_im/max(|v_im|,1e-12)>|,  v_im = pc[nbr[i][m]] - pc[i]

@@ -286,3 +286,67 @@ def test_nn_pair_filter_is_conservative(scale, shift):
         d1, j1, d2, i2 = ops.nn_pair(cu(adv), cu(ori), hint_a2o=hint)
         assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
         assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+
+
+def test_nn_pair_any_visiting_order():
+    """perm only changes the order in which points are visited (and enables bounding-box pruning when it is
+    spatially coherent): identity, Morton and random permutations, with lattice ties, clustered duplicates and
+    ragged sizes, must all return the oracle's result in ORIGINAL numbering."""
+    from geoa3_b200 import ops
+
+    rng = np.random.default_rng(21)
+    cases = []
+    adv, ori, _ = make(3, 1024, 4, 2e-2)
+    cases.append((adv, ori))
+    a2, _, _ = make(2, 777, 1, 1e-3)
+    _, o2, _ = make(2, 2500, 6, 1e-3)
+    cases.append((a2, o2))
+    lat, _ = synth.lattice_cloud(343)
+    cases.append((np.stack([lat, lat[:, ::-1].copy()]), np.stack([lat + 0.125, lat])))
+    for adv, ori in cases:
+        b, _, n = adv.shape
+        m = ori.shape[2]
+        od1, oj1 = O.nn1(adv, ori)
+        od2, oi2 = O.nn1(ori, adv)
+        A, Oc = cu(adv), cu(ori)
+        orders = {"morton": (ops.morton_order(A)[0], ops.morton_order(Oc)[0]),
+                  "random": (cu(np.stack([rng.permutation(n) for _ in range(b)]).astype(np.int32)),
+                             cu(np.stack([rng.permutation(m) for _ in range(b)]).astype(np.int32)))}
+        garbage = torch.from_numpy(rng.integers(0, min(n, m), (b, n)).astype(np.int32)).cuda()
+        for name, (pa, po) in orders.items():
+            inv = lambda p: torch.empty_like(p).scatter_(1, p.long(), torch.arange(p.shape[1], device="cuda", dtype=torch.int32).expand_as(p).contiguous())
+            for kw in ({}, {"iperm_a": inv(pa), "iperm_o": inv(po), "hint_a2o": cu(oj1), "hint_o2a": cu(oi2)},
+                       {"iperm_a": inv(pa), "iperm_o": inv(po), "hint_a2o": garbage}, {"hint_a2o": cu(oj1)}):
+                d1, j1, d2, i2 = ops.nn_pair(A, Oc, perm_a=pa, perm_o=po, **kw)
+                assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2), (name, list(kw))
+                assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2), (name, list(kw))
+
+
+def test_knn_any_visiting_order():
+    """kNN with visiting orders (identity / Morton / random), hinted and unhinted, on smooth clouds, lattice ties
+    and duplicated points: always the oracle's lexicographic (dist, original index) result."""
+    from geoa3_b200 import ops
+
+    rng = np.random.default_rng(31)
+    clouds_ = [make(3, 1024, 2, 2e-2)[0], make(2, 1500, 5, 1e-2)[0]]
+    lat, _ = synth.lattice_cloud(343)
+    clouds_.append(np.stack([lat, lat * 0.5]))
+    dup = clouds_[0][:2, :, :300].copy()
+    dup[:, :, 150:200] = dup[:, :, 0:50]
+    clouds_.append(np.ascontiguousarray(dup))
+    for pts in clouds_:
+        b, _, n = pts.shape
+        P = cu(pts)
+        pm, ipm = ops.morton_order(P)
+        pr = cu(np.stack([rng.permutation(n) for _ in range(b)]).astype(np.int32))
+        ipr = torch.empty_like(pr)
+        ipr.scatter_(1, pr.long(), torch.arange(n, device="cuda", dtype=torch.int32).expand(b, n).contiguous())
+        for K in (17, 33, 4):
+            oi, od = O.knn(pts, pts, K)
+            hint = cu(np.ascontiguousarray(oi[:, :, 1:]))
+            for name, (pq, pc, ipc) in {"morton": (pm, pm, ipm), "random": (pr, pr, ipr), "noinv": (pm, pm, None),
+                                       "cand_only": (None, pm, ipm)}.items():
+                for h in (None, hint):
+                    idx, dist = ops.knn(P, P, K, return_dist=True, hint=h, perm_q=pq, perm_c=pc, iperm_c=ipc)
+                    assert np.array_equal(idx.cpu().numpy(), oi), (name, K, h is not None)
+                    assert np.array_equal(dist.cpu().numpy(), od), (name, K, h is not None)

@@ -44,6 +44,10 @@ def sweep():
             hn = ops.knn(prev, prev, k + 1, drop=1)[0]
             t_knn = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1), iters=5, warm=2)
             t_hint = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), iters=5, warm=2)
+            pm, ipm = ops.morton_order(ori)
+            t_mort = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm), iters=5, warm=2)
+            assert torch.equal(ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm)[0],
+                               ops.knn(adv, adv, k + 1, drop=1)[0])
             nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
             assert torch.equal(nbr, ops.knn(adv, adv, k + 1, drop=1)[0])
             _, js, _, _ = ops.nn_pair(adv, ori)
@@ -51,7 +55,8 @@ def sweep():
             byts = (28 + 4 * k) * B * n
             flop = 8.0 * B * n * n
             print(json.dumps(dict(what="curvature_sweep", B=B, n=n, k=k, knn_us=round(t_knn[0], 1),
-                                  knn_hinted_us=round(t_hint[0], 1), kappa_us=round(t_kap[0], 1),
+                                  knn_hinted_us=round(t_hint[0], 1), knn_hinted_morton_us=round(t_mort[0], 1),
+                                  kappa_us=round(t_kap[0], 1),
                                   hbm_frac=round(byts / ((t_hint[0] + t_kap[0]) * 1e-6) / 6555.2e9, 5),
                                   fp32_tflops_hinted=round(flop / (t_hint[0] * 1e-6) / 1e12, 2))))
 
@@ -77,6 +82,13 @@ def main():
     res["nn_pair"] = timeit(lambda: ops.nn_pair(adv, ori), flush=flush)
     d1, js, d2, is_ = ops.nn_pair(adv, ori)
     res["nn_pair_hinted"] = timeit(lambda: ops.nn_pair(adv, ori, hint_a2o=js, hint_o2a=is_), flush=flush)
+    perm, iperm = ops.morton_order(ori)
+    ori_s = ops.arrange(ori, perm)
+    mk = dict(hint_a2o=js, hint_o2a=is_, perm_a=perm, perm_o=perm, iperm_a=iperm, iperm_o=iperm, ori_arranged=ori_s)
+    res["nn_pair_morton(incl. gather of adv)"] = timeit(lambda: ops.nn_pair(adv, ori, **mk), flush=flush)
+    chk = ops.nn_pair(adv, ori, **mk)
+    assert torch.equal(chk[1], js) and torch.equal(chk[3], is_) and torch.equal(chk[0], d1)
+    perm, iperm = ops.morton_order(ori)
     res["knn_self"] = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1), flush=flush)
     nbr = ops.knn(adv, adv, k + 1, drop=1)[0]
     # hint = neighbours of the previous attack step (adv moved by one Adam step ~ lr*sign = 0.01 per coordinate at most)
@@ -84,6 +96,10 @@ def main():
     nbr_prev = ops.knn(adv_prev, adv_prev, k + 1, drop=1)[0]
     res["knn_self_hinted"] = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev), flush=flush)
     assert torch.equal(ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev)[0], nbr)
+    perm, iperm = ops.morton_order(ori)
+    res["knn_self_morton(incl. gather)"] = timeit(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev, perm_q=perm, perm_c=perm,
+                                                    iperm_c=iperm), flush=flush)
+    assert torch.equal(ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev, perm_q=perm, perm_c=perm, iperm_c=iperm)[0], nbr)
     nbr_o = ops.knn(ori, ori, k + 1, drop=1)[0]
     ko = ops.kappa_loss_fwd(ori, normal=nrm, nbr=nbr_o)["kappa"]
     f = lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr, d_a2o=d1, d_o2a=d2, kappa_ori=ko, want_nrm=True,
