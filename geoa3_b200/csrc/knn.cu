@@ -70,12 +70,13 @@ template <int K, bool PRUNE>
 __global__ void __launch_bounds__(KNN_THREADS, K <= 17 ? 6 : 4)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n, int m, int kout, int drop,
            const int32_t* __restrict__ perm_q, const int32_t* __restrict__ perm_c, const int32_t* __restrict__ iperm_c,
-           const int32_t* hint, int hint_k, int32_t* idx_out, float* __restrict__ dist_out) {
+           const float* __restrict__ bb_c, const int32_t* hint, int hint_k, int32_t* idx_out,
+           float* __restrict__ dist_out) {
   __shared__ __align__(16) float sx[KNN_CHUNK];
   __shared__ __align__(16) float sy[KNN_CHUNK];
   __shared__ __align__(16) float sz[KNN_CHUNK];
   __shared__ int so[PRUNE ? KNN_CHUNK : 1];             // original index of the staged candidate
-  __shared__ float sbb[PRUNE ? KNN_CHUNK / 32 : 1][6];  // bounding box of every 32-candidate group
+  __shared__ __align__(16) float sbb[PRUNE ? KNN_CHUNK / 32 : 1][8];  // bounding boxes of the staged 32-candidate groups
   __shared__ int qj[KNN_QDEPTH][KNN_THREADS];
 
   const int cloud = blockIdx.y;
@@ -96,12 +97,27 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   float tau0 = KNN_INF;
   const bool use_hint = hint != nullptr && hint_k + 1 >= K && (!pc || ipc);
 
+  const int G0 = (m + 31) >> 5;  // level-0 boxes (32 candidates), followed by level-1 boxes (KNN_CHUNK candidates)
+  const float* bbc = (PRUNE && bb_c) ? bb_c + (size_t)cloud * (G0 + (m + KNN_CHUNK - 1) / KNN_CHUNK) * 8 : nullptr;
+  if (PRUNE && use_hint) {
+    // chunks may be skipped before they are ever staged, so the hinted bound is evaluated up front from the
+    // arranged cloud in global memory (positions through the inverse permutation)
+    const int32_t* h = hint + ((size_t)cloud * n + qq) * hint_k;  // may alias idx_out: own row, read before write
+    auto cand_d = [&](int j) {
+      const int pos = ipc[min(max(j, 0), m - 1)];
+      return dist2(cbase[pos], cbase[m + pos], cbase[2 * m + pos], qx, qy, qz);
+    };
+    float mx = cand_d(qq);
+    for (int t = 0; t < hint_k; ++t) mx = fmaxf(mx, cand_d(h[t]));
+    if (mx < 3.0e38f) tau0 = mx;
+  }
+
   TopK<K> top;
   bool rescan = false;
   do {
   top.init();
   float tau = tau0;  // candidates with d <= tau are worth an exact look
-  bool hint_pending = use_hint && !rescan;
+  bool hint_pending = !PRUNE && use_hint && !rescan;
   // 32-bit shared-window address of this thread's queue column, kept in ONE register: the compiler otherwise
   // re-materialises the base (3 extra predicated instructions per candidate)
   const unsigned q0 = (unsigned)__cvta_generic_to_shared(&qj[0][tid]);
@@ -131,29 +147,24 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   for (c0 = 0; c0 < m; c0 += KNN_CHUNK) {
     const int cn = min(KNN_CHUNK, m - c0);
     const int cn32 = (cn + 31) & ~31;
-    __syncthreads();
-    for (int t = tid; t < cn32; t += KNN_THREADS) {  // a warp stages 32 consecutive positions = one group
+    if (PRUNE) {  // whole chunk out of reach of every query of this CTA?  then it is never even staged
+      const float* cb = bbc + (size_t)(G0 + c0 / KNN_CHUNK) * 8;
+      const float ex = fmaxf(fmaxf(cb[0] - qx, qx - cb[3]), 0.f);
+      const float ey = fmaxf(fmaxf(cb[1] - qy, qy - cb[4]), 0.f);
+      const float ez = fmaxf(fmaxf(cb[2] - qz, qz - cb[5]), 0.f);
+      if (!__syncthreads_or(live && (ex * ex + ey * ey + ez * ez) * 0.9999f <= tau)) continue;
+    } else {
+      __syncthreads();
+    }
+    for (int t = tid; t < cn32; t += KNN_THREADS) {
       const bool ok = t < cn;
-      const int o = ok ? (pc ? pc[c0 + t] : c0 + t) : 0;
       sx[t] = ok ? cbase[c0 + t] : KNN_INF;  // +inf padding: d = +inf never passes (ref is stored by position)
       sy[t] = ok ? cbase[m + c0 + t] : 0.f;
       sz[t] = ok ? cbase[2 * m + c0 + t] : 0.f;
-      if (PRUNE) {
-        so[t] = o;
-        float lx = ok ? sx[t] : 3e38f, ly = ok ? sy[t] : 3e38f, lz = ok ? sz[t] : 3e38f;
-        float hx = ok ? sx[t] : -3e38f, hy = ok ? sy[t] : -3e38f, hz = ok ? sz[t] : -3e38f;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-          lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, s)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, s));
-          ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, s)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, s));
-          lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, s)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, s));
-        }
-        if (lane == 0) {
-          float* bb = sbb[t >> 5];
-          bb[0] = lx; bb[1] = ly; bb[2] = lz; bb[3] = hx; bb[4] = hy; bb[5] = hz;
-        }
-      }
+      if (PRUNE) so[t] = ok ? pc[c0 + t] : 0;
     }
+    if (PRUNE)  // the chunk's level-0 boxes (precomputed by group_bbox_kernel), coalesced
+      for (int t = tid; t < (cn32 >> 5) * 8; t += KNN_THREADS) (&sbb[0][0])[t] = bbc[(size_t)(c0 >> 5) * 8 + t];
     __syncthreads();
     if (hint_pending) {
       // tau0 = max exact distance to the hinted candidates and to the point with the query's own index (the
@@ -234,25 +245,87 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
 
 template <int K>
 static int launch_knn(const float* query, const float* ref, int b, int n, int m, int kout, int drop,
-                      const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const int32_t* hint,
-                      int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
+                      const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const float* bb_c,
+                      const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
   dim3 grid(ceil_div(n, KNN_THREADS), b, 1);
   if (perm_c)
-    knn_kernel<K, true><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, perm_q, perm_c, iperm_c, hint, hint_k,
-                                                     idx, dist);
+    knn_kernel<K, true><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, perm_q, perm_c, iperm_c, bb_c, hint,
+                                                     hint_k, idx, dist);
   else
-    knn_kernel<K, false><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, perm_q, nullptr, nullptr, hint,
-                                                      hint_k, idx, dist);
+    knn_kernel<K, false><<<grid, KNN_THREADS, 0, s>>>(query, ref, n, m, kout, drop, perm_q, nullptr, nullptr, nullptr,
+                                                      hint, hint_k, idx, dist);
   return GEOA3_LAUNCH_RESULT();
+}
+
+// Bounding boxes of an arranged cloud: level 0 = every 32 consecutive positions, level 1 = every KNN_CHUNK.
+// bb layout per cloud: [G0 + G1][8] floats = lo xyz, hi xyz, max |p|^2, pad.
+__global__ void group_bbox_kernel(const float* __restrict__ pc, int n, float* __restrict__ bb) {
+  const int cloud = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int G0 = (n + 31) >> 5, G1 = (n + KNN_CHUNK - 1) / KNN_CHUNK;
+  const float* p = pc + (size_t)cloud * 3 * n;
+  float* out = bb + (size_t)cloud * (G0 + G1) * 8;
+  const int per = KNN_CHUNK / 32;                 // level-0 groups per level-1 box; one CTA (32 warps) per level-1 box
+  const int g1 = blockIdx.x;
+  __shared__ float s_box[32][8];
+  float lx = 3e38f, ly = 3e38f, lz = 3e38f, hx = -3e38f, hy = -3e38f, hz = -3e38f, w2 = 0.f;
+  const int g = g1 * per + wib;
+  const int t = g * 32 + lane;
+  if (g < G0 && t < n) {
+    const float x = p[t], y = p[n + t], z = p[2 * n + t];
+    lx = hx = x; ly = hy = y; lz = hz = z; w2 = x * x + y * y + z * z;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, s)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, s));
+    ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, s)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, s));
+    lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, s)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, s));
+    w2 = fmaxf(w2, __shfl_xor_sync(0xffffffffu, w2, s));
+  }
+  if (lane == 0) {
+    float* o = s_box[wib];
+    o[0] = lx; o[1] = ly; o[2] = lz; o[3] = hx; o[4] = hy; o[5] = hz; o[6] = w2; o[7] = 0.f;
+    if (g < G0)
+      for (int i = 0; i < 8; ++i) out[(size_t)g * 8 + i] = o[i];
+  }
+  __syncthreads();
+  if (wib == 0) {  // level 1: union of this CTA's 32 level-0 boxes
+    const float* o = s_box[lane];
+    lx = o[0]; ly = o[1]; lz = o[2]; hx = o[3]; hy = o[4]; hz = o[5]; w2 = o[6];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, s)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, s));
+      ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, s)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, s));
+      lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, s)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, s));
+      w2 = fmaxf(w2, __shfl_xor_sync(0xffffffffu, w2, s));
+    }
+    if (lane == 0) {
+      float* o1 = out + (size_t)(G0 + g1) * 8;
+      o1[0] = lx; o1[1] = ly; o1[2] = lz; o1[3] = hx; o1[4] = hy; o1[5] = hz; o1[6] = w2; o1[7] = 0.f;
+    }
+  }
 }
 
 }  // namespace geoa3
 
+extern "C" size_t geoa3_group_bbox_floats(int n) {
+  return (size_t)(((n + 31) >> 5) + (n + geoa3::KNN_CHUNK - 1) / geoa3::KNN_CHUNK) * 8;
+}
+
+extern "C" int geoa3_group_bbox(const float* pc_arranged, int b, int n, float* bb, geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(pc_arranged && bb && b > 0 && n > 0);
+  if (b > 65535) return GEOA3_EUNSUPPORTED;
+  static_assert(KNN_CHUNK == 1024, "one 1024-thread CTA per level-1 box");
+  group_bbox_kernel<<<dim3((n + KNN_CHUNK - 1) / KNN_CHUNK, b), 1024, 0, (cudaStream_t)stream>>>(pc_arranged, n, bb);
+  return GEOA3_LAUNCH_RESULT();
+}
+
 extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int m, int K, int drop,
-                         const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const int32_t* hint,
-                         int hint_k, int32_t* idx, float* dist, geoa3_stream_t stream) {
+                         const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const float* bb_c,
+                         const int32_t* hint, int hint_k, int32_t* idx, float* dist, geoa3_stream_t stream) {
   using namespace geoa3;
   GEOA3_CHECK_ARG(query && ref && idx);
+  GEOA3_CHECK_ARG((perm_c == nullptr) == (bb_c == nullptr));  // an arranged ref comes with its boxes
   GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
   if (K > GEOA3_KNN_MAX_K || b > 65535) return GEOA3_EUNSUPPORTED;
   if (K > m) return GEOA3_EINVAL;
@@ -260,7 +333,7 @@ extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int
   const int kout = K - drop;
   // the list size is a compile-time constant (register arrays); a larger list than requested is still
   // exact: the first K entries of the top-K' (K' >= K) are the top-K.
-#define GEOA3_KNN_ARGS query, ref, b, n, m, kout, drop, perm_q, perm_c, iperm_c, hint, hint_k, idx, dist, s
+#define GEOA3_KNN_ARGS query, ref, b, n, m, kout, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx, dist, s
   if (K <= 3) return launch_knn<3>(GEOA3_KNN_ARGS);
   if (K <= 5) return launch_knn<5>(GEOA3_KNN_ARGS);
   if (K <= 9) return launch_knn<9>(GEOA3_KNN_ARGS);

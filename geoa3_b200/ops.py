@@ -81,6 +81,18 @@ def nn_pair(adv, ori, both=True, hint_a2o=None, hint_o2a=None, out=None, perm_a=
     return d1, j1, d2, i2
 
 
+def group_bbox(pc_arranged):
+    """pc [b,3,n] already in visiting order -> boxes [b, G0+G1, 8] (see include/geoa3_b200.h)."""
+    require_cuda_f32(pc_arranged, "pc_arranged")
+    b, _, n = pc_arranged.shape
+    nf = _lib.load().geoa3_group_bbox_floats(n)
+    bb = torch.empty(b, nf // 8, 8, device=pc_arranged.device, dtype=torch.float32)
+    with _guard(pc_arranged):
+        _count(1)
+        check(_lib.load().geoa3_group_bbox(ptr(pc_arranged), b, n, ptr(bb), stream(pc_arranged)))
+    return bb
+
+
 def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=None, perm_c=None, iperm_c=None):
     """query [b,3,n], ref [b,3,m] -> idx [b,n,K-drop] i32 (ascending (dist,idx)), dist | None.
     hint [b,n,hk] int32 (optional) only tightens the start threshold (exact for any hint); `out` may be the
@@ -89,10 +101,12 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=No
     b, _, n = query.shape
     m = ref.shape[2]
     idx = out if out is not None else torch.empty(b, n, K - drop, device=query.device, dtype=torch.int32)
-    if perm_c is not None:  # arrange the clouds in visiting order (coalesced staging in the kernel)
+    bb = None
+    if perm_c is not None:  # arrange the clouds in visiting order (coalesced staging) and box the ref groups
         same = query is ref and perm_q is perm_c
         ref = arrange(ref, perm_c)
         query = ref if same else (arrange(query, perm_q) if perm_q is not None else query)
+        bb = group_bbox(ref)
     elif perm_q is not None:
         query = arrange(query, perm_q)
     hk = 0
@@ -103,7 +117,7 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=No
     with _guard(query):
         _count(1)
         check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(perm_q), ptr(perm_c), ptr(iperm_c),
-                                    ptr(hint), hk, ptr(idx), ptr(dist), stream(query)))
+                                    ptr(bb), ptr(hint), hk, ptr(idx), ptr(dist), stream(query)))
     return idx, dist
 
 

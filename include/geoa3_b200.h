@@ -81,8 +81,15 @@ GEOA3_API int geoa3_nn_pair(const float *adv, const float *ori, int b, int n, in
  * original numbering and identical for any permutation; a spatially coherent one enables bounding-box pruning.
  * Replaces: knn_points(pc, pc, K=k+1).idx[..., 1:], Lib/loss_utils.py:57-58,77-78,139,174. */
 GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int m, int K, int drop,
-                        const int32_t *perm_q, const int32_t *perm_c, const int32_t *iperm_c, const int32_t *hint,
-                        int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
+                        const int32_t *perm_q, const int32_t *perm_c, const int32_t *iperm_c, const float *bb_c,
+                        const int32_t *hint, int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
+
+/* Bounding boxes of a cloud that is already arranged in visiting order: per cloud geoa3_group_bbox_floats(n)
+ * floats = [G0 + G1][8] (lo xyz, hi xyz, max |p|^2, pad), G0 = ceil(n/32) boxes of 32 consecutive positions
+ * followed by G1 = ceil(n/1024) boxes of 1024.  Input to geoa3_knn's `bb_c` (required with perm_c): whole
+ * 1024-candidate chunks are skipped before they are staged, then 32-candidate groups inside a staged chunk. */
+GEOA3_API size_t geoa3_group_bbox_floats(int n);
+GEOA3_API int geoa3_group_bbox(const float *pc_arranged, int b, int n, float *bb, geoa3_stream_t stream);
 
 /* Local curvature + per-cloud loss reductions, one CTA per cloud, fixed-order reductions.
  *   kappa_i = (1/k) sum_m |<nrm_i, v_im/max(|v_im|,1e-12)>|,  v_im = pc[nbr[i][m]] - pc[i]

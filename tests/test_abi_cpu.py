@@ -35,7 +35,7 @@ def test_argument_errors_do_not_need_a_gpu():
 
     lib = _lib.load()
     assert lib.geoa3_nn_pair(None, None, 1, 8, 8, *([None] * 11)) == -1
-    assert lib.geoa3_knn(None, None, 0, 0, 0, 1, 0, None, None, None, None, 0, None, None, None) == -1
+    assert lib.geoa3_knn(None, None, 0, 0, 0, 1, 0, None, None, None, None, None, 0, None, None, None) == -1
     assert lib.geoa3_group_points_grad_workspace_bytes(2, 10, 4, 3) == 16 + 2 * (10 + 1 + 12) * 4
 
 
