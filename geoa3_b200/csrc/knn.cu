@@ -77,7 +77,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   __shared__ __align__(16) float sz[KNN_CHUNK];
   __shared__ int so[PRUNE ? KNN_CHUNK : 1];             // original index of the staged candidate
   __shared__ __align__(16) float sbb[PRUNE ? KNN_CHUNK / 32 : 1][8];  // bounding boxes of the staged 32-candidate groups
-  __shared__ int qj[KNN_QDEPTH][KNN_THREADS];
+  __shared__ uint16_t qj[KNN_QDEPTH][KNN_THREADS];  // positions inside the staged chunk (< KNN_CHUNK)
 
   const int cloud = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -121,7 +121,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
   // 32-bit shared-window address of this thread's queue column, kept in ONE register: the compiler otherwise
   // re-materialises the base (3 extra predicated instructions per candidate)
   const unsigned q0 = (unsigned)__cvta_generic_to_shared(&qj[0][tid]);
-  constexpr unsigned QSTRIDE = KNN_THREADS * sizeof(int);
+  constexpr unsigned QSTRIDE = KNN_THREADS * sizeof(uint16_t);
   unsigned qa = q0;
   int c0 = 0;
 
@@ -217,7 +217,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int n
       while (mask) {  // bit 31 is position j, bit 0 is position j+31: ascending position = descending bit
         const int t = __clz(mask);
         mask &= ~(0x80000000u >> t);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(j + t) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(j + t)) : "memory");
         qa += QSTRIDE;
       }
       if (__any_sync(0xffffffffu, qa > q0 + (KNN_QDEPTH - 32) * QSTRIDE)) drain();
