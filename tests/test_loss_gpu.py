@@ -350,3 +350,44 @@ def test_knn_any_visiting_order():
                     idx, dist = ops.knn(P, P, K, return_dist=True, hint=h, perm_q=pq, perm_c=pc, iperm_c=ipc)
                     assert np.array_equal(idx.cpu().numpy(), oi), (name, K, h is not None)
                     assert np.array_equal(dist.cpu().numpy(), od), (name, K, h is not None)
+
+
+def test_api_ragged_sizes_and_small_k():
+    """Reference API with n != m (Chamfer / Hausdorff between clouds of different sizes) and the reference's
+    default k=2 (K=3 list), values and gradients against the oracle."""
+    from geoa3_b200 import loss_utils as L
+
+    rng = np.random.default_rng(8)
+    adv = rng.standard_normal((2, 3, 300)).astype(np.float32) * 0.5
+    ori = rng.standard_normal((2, 3, 517)).astype(np.float32) * 0.5
+    a = cu(adv).requires_grad_(True)
+    cd = L.chamfer_loss(a, cu(ori))
+    hd = L.hausdorff_loss(a, cu(ori))
+    (cd + 0.5 * hd).sum().backward()
+    d1, j1 = O.nn1(adv, ori)
+    d2, i2 = O.nn1(ori, adv)
+    assert rel_err(cd.detach().cpu().numpy(), d1.astype(np.float64).mean(1) + d2.astype(np.float64).mean(1)) < TOL
+    assert rel_err(hd.detach().cpu().numpy(), d1.max(1)) < TOL
+    G = np.zeros((2, 3, 300))
+    for c in range(2):
+        A, Oo = adv[c].astype(np.float64), ori[c].astype(np.float64)
+        G[c] += 2.0 / 300 * (A - Oo[:, j1[c]])
+        for j in range(517):
+            G[c][:, i2[c, j]] += 2.0 / 517 * (A[:, i2[c, j]] - Oo[:, j])
+        ih = int(np.argmax(d1[c]))
+        G[c][:, ih] += 0.5 * 2.0 * (A[:, ih] - Oo[:, j1[c, ih]])
+    assert rel_err(a.grad.cpu().numpy(), G) < TOL
+    # default k=2 curvature path
+    pc, nr, _ = synth.make_batch(2, 200, 3)
+    adv2 = pc + synth.make_offsets(2, 200, std=1e-2)
+    ko = L._get_kappa_ori(cu(pc), cu(nr))
+    kap_o, _ = O.kappa_ori(pc, nr, 2)
+    assert rel_err(ko.cpu().numpy(), kap_o) < TOL
+    a2 = cu(adv2).requires_grad_(True)
+    ka, nrm_adv = L._get_kappa_adv(a2, cu(pc), cu(nr))
+    cu_ = L.curvature_loss(a2, cu(pc), ka, ko)
+    cu_.sum().backward()
+    fwd = O.geo_forward(adv2, pc, nr, ko.cpu().numpy(), 2)
+    assert rel_err(cu_.detach().cpu().numpy(), fwd["curv"]) < TOL
+    Gc = O.geo_backward(adv2, pc, fwd, ko.cpu().numpy(), 0.0, 0.0, 1.0)
+    assert rel_err(a2.grad.cpu().numpy(), Gc) < TOL
