@@ -498,6 +498,143 @@ group_grad_fwd_order_kernel(const float* __restrict__ grad_out, const int32_t* _
   }
 }
 
+// ---- row-structured variant: nsample = 32*SPR.  The generic kernel above spends its issue slots and LSU
+// wavefronts (ncu: LSU data pipe 83 %) on one 5-step shuffle tree + leader vote per SLICE and on bank-conflicted
+// 32-bit RMWs.  Here (a) the padding copies are summed once per ROW: position 0 of the row holds the first index
+// itself, so lane 0 of slice 0 is always the leader and no vote is needed; (b) the CC channel sums share ONE
+// butterfly (after the first exchange half the warp reduces channel 0 and the other half channel 1: 6 shuffles
+// for 2 channels instead of 10, 9 for 4 instead of 20); (c) the CC accumulators of a target are adjacent, so the
+// RMW is one LDS.64/128 + one STS.64/128; (d) the slices tile the index array linearly, so every load is a
+// running pointer + immediate.  All targets of a row except the padding are distinct => one __syncwarp per row.
+// sums z[0..CC) over the warp; lane 0 receives every total (other lanes: unspecified).  Fixed order.
+template <int CC>
+__device__ __forceinline__ void gf_reduce(float (&z)[CC], int lane) {
+  constexpr unsigned F = 0xffffffffu;
+  if constexpr (CC == 1) {
+    z[0] = warp_sum(z[0]);
+  } else if constexpr (CC == 2) {
+    const bool hi = lane & 16;
+    float keep = hi ? z[1] : z[0];
+    keep += __shfl_xor_sync(F, hi ? z[0] : z[1], 16);
+#pragma unroll
+    for (int o = 8; o; o >>= 1) keep += __shfl_xor_sync(F, keep, o);
+    z[0] = keep;                                  // valid on lanes 0..15
+    z[1] = __shfl_xor_sync(F, keep, 16);          // lanes 0..15 read channel 1 from the upper half
+  } else {
+    const bool h16 = lane & 16, h8 = lane & 8;
+    float a = h16 ? z[1] : z[0], b = h16 ? z[3] : z[2];
+    a += __shfl_xor_sync(F, h16 ? z[0] : z[1], 16);   // a: ch0 (low half) / ch1 (high half)
+    b += __shfl_xor_sync(F, h16 ? z[2] : z[3], 16);   // b: ch2 / ch3
+    float k = h8 ? b : a;
+    k += __shfl_xor_sync(F, h8 ? a : b, 8);           // lanes 0-7 ch0, 8-15 ch2, 16-23 ch1, 24-31 ch3
+#pragma unroll
+    for (int o = 4; o; o >>= 1) k += __shfl_xor_sync(F, k, o);
+    z[0] = k;
+    z[2] = __shfl_sync(F, k, 8);
+    z[1] = __shfl_sync(F, k, 16);
+    z[3] = __shfl_sync(F, k, 24);
+  }
+}
+
+template <int CC> __device__ __forceinline__ void lds_vec(float (&a)[CC], uint32_t addr) {
+  if constexpr (CC == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[0]) : "r"(addr) : "memory");
+  else if constexpr (CC == 2)
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a[0]), "=f"(a[1]) : "r"(addr) : "memory");
+  else
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]) : "r"(addr) : "memory");
+}
+template <int CC> __device__ __forceinline__ void sts_vec(uint32_t addr, const float (&a)[CC]) {
+  if constexpr (CC == 1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a[0]) : "memory");
+  else if constexpr (CC == 2)
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a[0]), "f"(a[1]) : "memory");
+  else
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3])
+                 : "memory");
+}
+
+template <int CC, int SPR>
+__global__ void __launch_bounds__(GF_THREADS)
+group_grad_rows_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ idx, int c, int n, int m,
+                       float* __restrict__ grad_points, const int* __restrict__ violations) {
+  extern __shared__ __align__(16) float gf_acc[];  // [GF_WARPS][n][CC]
+  if (*violations != 0) return;
+  constexpr int NS = 32 * SPR;
+  constexpr int R = SPR >= 4 ? 1 : 4 / SPR;       // rows in flight per iteration (4 slices of loads)
+  const int cloud = blockIdx.y, c0 = blockIdx.x * CC, cc = min(CC, c - c0);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < GF_WARPS * CC * n; i += GF_THREADS) gf_acc[i] = 0.f;
+  __syncthreads();
+  // one 32-bit shared address per warp; the RMWs below are explicit ld/st.shared so that the compiler does not
+  // rebuild a generic pointer per access
+  const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(gf_acc) + (uint32_t)w * (uint32_t)n * (4u * CC);
+  const size_t E = (size_t)m * NS;
+  const int rows_per_warp = (m + GF_WARPS - 1) / GF_WARPS;
+  const int j_beg = min(m, w * rows_per_warp), j_end = min(m, j_beg + rows_per_warp);
+  const int32_t* ixp = idx + (size_t)cloud * E + (size_t)j_beg * NS + lane;
+  const float* gop[CC];
+#pragma unroll
+  for (int l = 0; l < CC; ++l)
+    gop[l] = grad_out + ((size_t)cloud * c + c0 + min(l, cc - 1)) * E + (size_t)j_beg * NS + lane;
+#pragma unroll
+  for (int l = 0; l < CC; ++l) asm volatile("" : "+l"(gop[l]));  // opaque: keeps the bases out of the loop body
+  for (int j = j_beg; j < j_end; j += R) {
+    int p[R][SPR];
+    float v[R][SPR][CC];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool live = j + r < j_end;
+#pragma unroll
+      for (int sl = 0; sl < SPR; ++sl) {
+        p[r][sl] = live ? ixp[(r * SPR + sl) * 32] : -1;
+#pragma unroll
+        for (int l = 0; l < CC; ++l) v[r][sl][l] = live ? __ldcs(gop[l] + (r * SPR + sl) * 32) : 0.f;
+      }
+    }
+    ixp += R * NS;
+#pragma unroll
+    for (int l = 0; l < CC; ++l) gop[l] += R * NS;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int p0 = __shfl_sync(0xffffffffu, p[r][0], 0);
+      bool is0[SPR];
+      float z[CC];
+#pragma unroll
+      for (int sl = 0; sl < SPR; ++sl) {
+        is0[sl] = p[r][sl] == p0;
+#pragma unroll
+        for (int l = 0; l < CC; ++l) {
+          const float t = is0[sl] ? v[r][sl][l] : 0.f;
+          z[l] = sl ? z[l] + t : t;
+        }
+      }
+      gf_reduce<CC>(z, lane);
+#pragma unroll
+      for (int sl = 0; sl < SPR; ++sl) {
+        const bool lead = sl == 0 && lane == 0;      // holds the row's first index itself
+        if (p[r][sl] >= 0 && (!is0[sl] || lead)) {
+          float a[CC];
+          const uint32_t addr = acc_s + (uint32_t)p[r][sl] * (4u * CC);
+          lds_vec<CC>(a, addr);
+#pragma unroll
+          for (int l = 0; l < CC; ++l) a[l] += lead ? z[l] : v[r][sl][l];
+          sts_vec<CC>(addr, a);
+        }
+      }
+      __syncwarp();  // the next row may touch the same targets from other lanes
+    }
+  }
+  __syncthreads();
+  float* gp = grad_points + ((size_t)cloud * c + c0) * n;
+  for (int i = tid; i < cc * n; i += GF_THREADS) {
+    const int l = i / n, t = i - l * n;
+    float sacc = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < GF_WARPS; ++ww) sacc += gf_acc[((size_t)ww * n + t) * CC + l];
+    gp[i] = sacc;
+  }
+}
+
 // ============================================================================ gather_points (+grad)
 __global__ void gather_points_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx, int c, int n,
                                      int m, float* __restrict__ out) {
@@ -624,6 +761,29 @@ static int launch_fwd_order(const float* grad_out, const int32_t* idx, int b, in
   return GEOA3_LAUNCH_RESULT();
 }
 
+template <int CC, int SPR>
+static int launch_rows_t(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, float* grad_points,
+                         const int* flag, cudaStream_t s) {
+  const size_t smem = (size_t)GF_WARPS * CC * n * 4;
+  cudaError_t e = cudaFuncSetAttribute(group_grad_rows_kernel<CC, SPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  group_grad_rows_kernel<CC, SPR><<<dim3(ceil_div(c, CC), b), GF_THREADS, smem, s>>>(grad_out, idx, c, n, m,
+                                                                                    grad_points, flag);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+static int launch_rows(int CC, int SPR, const float* grad_out, const int32_t* idx, int b, int c, int n, int m,
+                       float* grad_points, const int* flag, cudaStream_t s) {
+#define GF_ROWS_CASE(cc_, spr_) \
+  if (CC == cc_ && SPR == spr_) return launch_rows_t<cc_, spr_>(grad_out, idx, b, c, n, m, grad_points, flag, s)
+  GF_ROWS_CASE(1, 1); GF_ROWS_CASE(1, 2); GF_ROWS_CASE(1, 4);
+  GF_ROWS_CASE(2, 1); GF_ROWS_CASE(2, 2); GF_ROWS_CASE(2, 4);
+  GF_ROWS_CASE(4, 1); GF_ROWS_CASE(4, 2); GF_ROWS_CASE(4, 4);
+#undef GF_ROWS_CASE
+  return GEOA3_EUNSUPPORTED;
+}
+
 // group_points_grad: forward-order kernel when every index row has the ball-query shape (checked on the device),
 // generic CSR path otherwise; both are launched, each exits immediately when it is not its turn.
 static int run_group_grad(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, int ns,
@@ -631,12 +791,18 @@ static int run_group_grad(const float* grad_out, const int32_t* idx, int b, int 
   const int E = m * ns;
   if (workspace_bytes < csr_ws_bytes(b, n, E) || !workspace) return GEOA3_EWORKSPACE;
   int* flag = (int*)workspace;
-  // channels per CTA: measured best on B200 is 2 (4 KB of private accumulators per warp at n = 512 keeps ~50 warps
-  // resident per SM; 4 or 8 channels amortise the index handling better but starve the SM of warps)
+  // channels per CTA.  Generic kernel: 2 measured best (4 KB of private accumulators per warp at n = 512 keeps ~50
+  // warps resident per SM).  Row-structured kernel (nsample 32/64/128): 4 when >= 3 CTAs/SM still fit (fewer
+  // shuffles and RMW instructions per channel), 1 for the xyz-only case where 4 would leave the grid too small.
+  const bool rows_kernel = ns == 32 || ns == 64 || ns == 128;
   int CC = 0;
   if ((size_t)GF_WARPS * 2 * n * 4 <= 100 * 1024) CC = 2;
   else if ((size_t)GF_WARPS * n * 4 <= 200 * 1024) CC = 1;
   if (!CC) return run_csr_grad(grad_out, nullptr, idx, b, c, n, E, 1, grad_points, workspace, workspace_bytes, s);
+  if (rows_kernel) {
+    if (c < 8) CC = 1;
+    else if ((size_t)GF_WARPS * 4 * n * 4 <= 72 * 1024) CC = 4;
+  }
   if (c == 1) CC = 1;
   if (const char* ov = getenv("GEOA3_GF_CC")) {  // tuning knob (tools/time_kernels.py), not part of the API
     const int v = atoi(ov);
@@ -647,6 +813,12 @@ static int run_group_grad(const float* grad_out, const int32_t* idx, int b, int 
   fwd_order_ok_kernel<<<ceil_div(b * m, 8), 256, 0, s>>>(idx, b * m, ns, n, flag);
   int err = GEOA3_LAUNCH_RESULT();
   if (err) return err;
+  if (rows_kernel) {
+    if (CC > 4) CC = 4;
+    err = launch_rows(CC, ns / 32, grad_out, idx, b, c, n, m, grad_points, flag, s);
+    if (err) return err;
+    return run_csr_grad(grad_out, nullptr, idx, b, c, n, E, 1, grad_points, workspace, workspace_bytes, s, flag);
+  }
   switch (CC) {
     case 8: err = launch_fwd_order<8>(grad_out, idx, b, c, n, m, ns, grad_points, flag, s); break;
     case 4: err = launch_fwd_order<4>(grad_out, idx, b, c, n, m, ns, grad_points, flag, s); break;

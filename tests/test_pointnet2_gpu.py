@@ -115,15 +115,20 @@ def test_fps_ulp_critical_vs_reference_binary():
         assert torch.equal(got, ext.furthest_point_sampling(cu(xyz), 256))
 
 
-@pytest.mark.parametrize("b,c,n,m,ns", [(4, 3, 1024, 512, 64), (4, 128, 512, 128, 64), (2, 67, 300, 50, 7),
-                                        (2, 320, 512, 128, 128)])
-def test_group_points_and_grad(b, c, n, m, ns):
+@pytest.mark.parametrize("b,c,n,m,ns,r", [(4, 3, 1024, 512, 64, 0.3), (4, 128, 512, 128, 64, 0.3),
+                                          (2, 67, 300, 50, 7, 0.3), (2, 320, 512, 128, 128, 0.3),
+                                          # row-structured backward: every slices-per-row / channels-per-CTA
+                                          # variant, odd row counts, channel tails, mostly-padding rows
+                                          (2, 9, 512, 50, 32, 0.3), (2, 16, 1024, 37, 32, 0.12),
+                                          (2, 10, 300, 33, 64, 0.08), (2, 6, 400, 21, 128, 0.5),
+                                          (2, 13, 2048, 19, 64, 0.2)])
+def test_group_points_and_grad(b, c, n, m, ns, r):
     from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
 
     rng = np.random.default_rng(0)
     xyz = clouds(b, n, 2)
     new = np.stack([xyz[i, O.fps(xyz[i:i + 1], m)[0]] for i in range(b)])
-    idx = O.ball_query(new, xyz, 0.3, ns)
+    idx = O.ball_query(new, xyz, r, ns)
     feats = rng.standard_normal((b, c, n)).astype(np.float32)
     f = cu(feats).requires_grad_(True)
     out = pu.grouping_operation(f, cu(idx))
