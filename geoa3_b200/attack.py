@@ -117,6 +117,9 @@ def forward_step(net, pc_ori, input_curr_iter, normal_ori, ori_kappa, target, sc
     if dtype_ == "L2":
         dis = loss_utils.norm_l2_loss(input_curr_iter, pc_ori)
         constrain = constrain + _get(cfg, "dis_loss_weight") * dis
+    if _get(cfg, "uniform_loss_weight") != 0:
+        # a batch-level scalar broadcast onto every instance, as in the reference (:169-171)
+        constrain = constrain + _get(cfg, "uniform_loss_weight") * loss_utils.uniform_loss(input_curr_iter)
     loss_n = cls_loss + scale_const * constrain
     loss = loss_n.sum() / float(loss_divisor if loss_divisor is not None else b)
     return logits, loss, loss_n, cls_loss, dis, hd, cu, constrain
@@ -305,8 +308,6 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
     for flag in ("is_partial_var", "is_subsample_opt", "is_pre_jitter_input"):
         if _get(cfg, flag):
             raise NotImplementedError("--%s is outside the B200 hot path (see DESIGN.md, out of scope)" % flag)
-    if _get(cfg, "uniform_loss_weight") != 0:
-        raise NotImplementedError("uniform_loss is broken in the reference (missing import, Lib/loss_utils.py:164)")
     device = device or torch.device("cuda", torch.cuda.current_device())
     targeted = _get(cfg, "attack_label") != "Untarget"
     pc_ori, normal_ori, target, gt_target = _unpack(input_data, cfg, device)

@@ -11,6 +11,13 @@ Same names, positional signatures, shapes and return conventions as the referenc
     _get_kappa_adv(adv_pc, ori_pc, ori_normal, k=2) -> ([b,n], [b,3,n])   Lib/loss_utils.py:64-82
     curvature_loss(adv_pc, ori_pc, adv_kappa, ori_kappa, k=2) -> [b]      Lib/loss_utils.py:84-97
 
+    displacement_loss(adv_pc, ori_pc, k=16)   -> [b,n]         Lib/loss_utils.py:99-107
+    corresponding_normal_loss(adv_pc, normal, k=2) -> [b,n]    Lib/loss_utils.py:109-117
+    repulsion_loss(pc, k=4, h=0.03)           -> [b,n]         Lib/loss_utils.py:119-123
+    distance_kmean_loss(pc, k)                -> [b,n]         Lib/loss_utils.py:125-133
+    kNN_smoothing_loss(adv_pc, k, threshold_coef=1.05) -> [b]  Lib/loss_utils.py:135-149
+    uniform_loss(adv_pc, percentages, radius=1.0, k=2) -> []   Lib/loss_utils.py:151-190
+
 All clouds are float32 CUDA tensors [b,3,n].  Where the reference launches four identical
 adv->ori 1-NN searches per step this module runs the fused bidirectional kernel once
 and shares the result through a per-step cache keyed on the adv tensor *object* (weakref + version
@@ -22,8 +29,15 @@ produced by one deterministic gather kernel per autograd node — no float atomi
 w_cd*CD + w_hd*HD + w_curv*CUR (the composition of Attacker/geoA3_attack.py:131-162) with a single
 backward launch.
 
+The second group (displacement ... uniform) are the regularisers the reference keeps next to the
+geometry-aware loss.  Their O(n^2) part — the neighbour search the reference does
+with a dense [b,n,n] matrix + topk or with pytorch3d — runs on the exact top-K kernel (and, for
+uniform_loss, on the FPS / ball_query / grouping kernels); the O(n*k) differentiable tail is the
+reference's own tensor algebra on the gathered neighbours.
+
 There is no CPU or pure-PyTorch fallback: a missing libgeoa3_b200.so or a CPU tensor raises.
 """
+import math
 import weakref
 
 import torch
@@ -31,7 +45,8 @@ import torch
 from . import ops
 
 __all__ = ["norm_l2_loss", "chamfer_loss", "pseudo_chamfer_loss", "hausdorff_loss", "_get_kappa_ori",
-           "_get_kappa_adv", "curvature_loss", "geo_loss", "clear_cache", "HintBuffers"]
+           "_get_kappa_adv", "curvature_loss", "displacement_loss", "corresponding_normal_loss", "repulsion_loss",
+           "distance_kmean_loss", "kNN_smoothing_loss", "uniform_loss", "geo_loss", "clear_cache", "HintBuffers"]
 
 
 # ---------------------------------------------------------------------------- search hints
@@ -325,6 +340,92 @@ def curvature_loss(adv_pc, ori_pc, adv_kappa, ori_kappa, k=2):
     e = _nn(_entry(adv_pc, ori_pc), True)
     onenn_ori_kappa = torch.gather(ori_kappa, 1, e.jstar.long())
     return ((adv_kappa - onenn_ori_kappa) ** 2).mean(-1)
+
+
+# ---------------------------------------------------------------------------- neighbourhood regularisers
+def _self_nbr(pc, k):
+    """Self kNN (K = k+1, own entry dropped like the reference's `[:, :, 1:]`) -> int64 [b,n,k]; no gradient,
+    exactly as topk / knn_points indices carry none."""
+    c = _as_input(pc.detach(), "pc")
+    return ops.knn(c, c, int(k) + 1, drop=1)[0].long()
+
+
+def _nbr_vectors(pc, nbr):
+    """pc [b,3,n], nbr [b,n,k] -> pc[nbr] - pc as [b,3,n,k], differentiable w.r.t. pc."""
+    b, _, n = pc.shape
+    k = nbr.shape[2]
+    nn_pts = torch.gather(pc, 2, nbr.reshape(b, 1, n * k).expand(b, 3, n * k)).view(b, 3, n, k)
+    return nn_pts - pc.unsqueeze(3)
+
+
+def displacement_loss(adv_pc, ori_pc, k=16):
+    """Variance-like penalty on the displacement magnitude among the k nearest ORIGINAL neighbours."""
+    b, _, n = adv_pc.shape
+    inter_idx = _self_nbr(ori_pc, k)
+    theta_distance = ((adv_pc - ori_pc) ** 2).sum(1)
+    nn_theta = torch.gather(theta_distance, 1, inter_idx.view(b, n * k)).view(b, n, k)
+    return ((nn_theta - theta_distance.unsqueeze(2)) ** 2).mean(2)
+
+
+def corresponding_normal_loss(adv_pc, normal, k=2):
+    """mean_m |<normal_i, unit(adv[nbr(i,m)] - adv_i)>| with the point's own normal."""
+    from .utility import _normalize
+
+    vectors = _normalize(_nbr_vectors(adv_pc, _self_nbr(adv_pc, k)))
+    return torch.abs((vectors * normal.unsqueeze(3)).sum(1)).mean(2)
+
+
+def repulsion_loss(pc, k=4, h=0.03):
+    dis = (_nbr_vectors(pc, _self_nbr(pc, k)) ** 2).sum(1)
+    return -(dis * torch.exp(-(dis ** 2) / (h ** 2))).mean(2)
+
+
+def distance_kmean_loss(pc, k):
+    b, _, n = pc.shape
+    nbr = _self_nbr(pc, k)
+    # the reference measures |p_i - p_j + 1e-12| (the epsilon is added to every coordinate difference, :127)
+    dis = ((1e-12 - _nbr_vectors(pc, nbr)) ** 2).sum(1).sqrt()
+    dis_mean = dis.mean(-1)
+    dis_mean_k = torch.gather(dis_mean, 1, nbr.view(b, n * k)).view(b, n, k)
+    return torch.abs(dis_mean.unsqueeze(2) - dis_mean_k).mean(-1)
+
+
+def kNN_smoothing_loss(adv_pc, k, threshold_coef=1.05):
+    knn_dis = (_nbr_vectors(adv_pc, _self_nbr(adv_pc, k)) ** 2).sum(1).mean(-1)
+    threshold = knn_dis.mean(-1) + threshold_coef * knn_dis.std(-1)
+    condition = torch.gt(knn_dis, threshold.unsqueeze(1)).float()
+    return (knn_dis * condition).mean(1)
+
+
+def uniform_loss(adv_pc, percentages=[0.004, 0.006, 0.008, 0.010, 0.012], radius=1.0, k=2):
+    """PU-GAN style uniformity term.  The reference body (Lib/loss_utils.py:151-190) needs `pointnet2_utils`,
+    which that file never imports; this is the function it evidently intends, on this package's own
+    pointnet2_ops.  The FPS seeds do not depend on the percentage and are computed once."""
+    from .pointnet2_ops import pointnet2_utils
+
+    if adv_pc.size(1) == 3:
+        adv_pc = adv_pc.permute(0, 2, 1).contiguous()
+    b, n, _ = adv_pc.size()
+    npoint = int(n * 0.05)
+    adv_pc_flipped = adv_pc.transpose(1, 2).contiguous()
+    seeds = pointnet2_utils.furthest_point_sample(adv_pc, npoint)
+    new_xyz = pointnet2_utils.gather_operation(adv_pc_flipped, seeds).transpose(1, 2).contiguous()
+    loss = None
+    for p in percentages:
+        p = p * 4
+        nsample = int(n * p)
+        r = math.sqrt(p * radius)
+        disk_area = math.pi * (radius ** 2) * p / nsample
+        expect_len = float(torch.sqrt(torch.tensor(disk_area, dtype=torch.float32)))  # fp32 like :161, host-side
+        idx = pointnet2_utils.ball_query(r, nsample, adv_pc, new_xyz)
+        grouped = pointnet2_utils.grouping_operation(adv_pc_flipped, idx)          # [b,3,npoint,nsample]
+        grouped = grouped.permute(0, 2, 1, 3).reshape(b * npoint, 3, nsample)     # one small cloud per patch
+        uniform_dis = (_nbr_vectors(grouped, _self_nbr(grouped, k)) ** 2).sum(1)    # [b*npoint,nsample,k]
+        uniform_dis = torch.sqrt(torch.abs(uniform_dis) + 1e-12).mean(-1)
+        uniform_dis = (uniform_dis - expect_len) ** 2 / (expect_len + 1e-12)
+        mean = uniform_dis.mean() * math.pow(p * 100, 2)
+        loss = mean if loss is None else loss + mean
+    return loss / len(percentages)
 
 
 def geo_loss(adv_pc, ori_pc, ori_normal, ori_kappa, k=16, w_cd=1.0, w_hd=0.1, w_curv=1.0, single_side=False,

@@ -148,6 +148,70 @@ def geo_backward(adv, ori, fwd, kap_ori, g_cd, g_hd, g_cu):
     return G
 
 
+# ------------------------------------------------------------------ neighbourhood regularisers
+def _nbr_vec(P, nbr):
+    """P [b,3,n] f32, nbr [b,n,k] -> P[nbr] - P as float64 [b,3,n,k]."""
+    P = np.asarray(P, np.float64)
+    b, _, n = P.shape
+    out = np.empty((b, 3, n, nbr.shape[2]), np.float64)
+    for i in range(b):
+        out[i] = P[i][:, nbr[i]] - P[i][:, :, None]
+    return out
+
+
+def aux_losses(adv, ori, normal, k, h=0.03, threshold_coef=1.05):
+    """Values (float64 tails on fp32-exact neighbour lists) of the reference's regularisers,
+    Lib/loss_utils.py:99-149: displacement, corresponding-normal, repulsion, distance-kmean, kNN smoothing."""
+    adv32, ori32 = _f32(adv), _f32(ori)
+    nbr_o = knn(ori32, ori32, k + 1)[0][:, :, 1:]
+    nbr_a = knn(adv32, adv32, k + 1)[0][:, :, 1:]
+    a, o, nr = (np.asarray(x, np.float64) for x in (adv32, ori32, normal))
+    b, _, n = a.shape
+    theta = ((a - o) ** 2).sum(1)                                                        # :105
+    nn_theta = np.stack([theta[i][nbr_o[i]] for i in range(b)])
+    out = dict(displacement=((nn_theta - theta[:, :, None]) ** 2).mean(2))               # :107
+    v = _nbr_vec(adv32, nbr_a)
+    L = np.maximum(np.sqrt((v ** 2).sum(1, keepdims=True)), 1e-12)
+    out["corr_normal"] = np.abs(((v / L) * nr[:, :, :, None]).sum(1)).mean(2)            # :115-117
+    dis = (v ** 2).sum(1)
+    out["repulsion"] = -(dis * np.exp(-(dis ** 2) / (h ** 2))).mean(2)                   # :123
+    dk = np.sqrt(((1e-12 - v) ** 2).sum(1))                                              # :127 (p_i - p_j + 1e-12)
+    dm = dk.mean(-1)
+    dmk = np.stack([dm[i][nbr_a[i]] for i in range(b)])
+    out["kmean"] = np.abs(dm[:, :, None] - dmk).mean(-1)                                 # :133
+    kd = dis.mean(-1)
+    thr = kd.mean(-1) + threshold_coef * kd.std(-1, ddof=1)                              # torch.std is unbiased
+    out["smoothing"] = (kd * (kd > thr[:, None])).mean(1)                                # :146-149
+    return out
+
+
+def uniform_loss(adv, percentages=(0.004, 0.006, 0.008, 0.010, 0.012), radius=1.0, k=2):
+    """Lib/loss_utils.py:151-190 with the pointnet2 calls it intends (fps / ball_query / group restated above)."""
+    import math
+
+    adv32 = _f32(adv)
+    b, _, n = adv32.shape
+    xyz = np.ascontiguousarray(adv32.transpose(0, 2, 1))
+    npoint = int(n * 0.05)
+    seeds = fps(xyz, npoint)
+    new_xyz = np.stack([xyz[i][seeds[i]] for i in range(b)])
+    total = 0.0
+    for p in percentages:
+        p = p * 4
+        nsample = int(n * p)
+        r = math.sqrt(p * radius)
+        expect_len = float(np.sqrt(np.float32(math.pi * (radius ** 2) * p / nsample)))   # fp32 tensor at :160-161
+        idx = ball_query(new_xyz, xyz, r, nsample)
+        patches = np.stack([xyz[i][idx[i]] for i in range(b)]).reshape(b * npoint, nsample, 3)
+        pt = np.ascontiguousarray(patches.transpose(0, 2, 1))
+        nb = knn(pt, pt, k + 1)[0][:, :, 1:]
+        d = (_nbr_vec(pt, nb) ** 2).sum(1)
+        u = np.sqrt(np.abs(d) + 1e-12).mean(-1)
+        u = (u - expect_len) ** 2 / (expect_len + 1e-12)
+        total += u.mean() * math.pow(p * 100, 2)
+    return total / len(percentages)
+
+
 # ------------------------------------------------------------------ pointnet2_ops
 def opt_n_threads(w):
     return lib().orc_opt_n_threads(int(w))

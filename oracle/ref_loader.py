@@ -107,3 +107,68 @@ def geo_loss_and_grad(adv, ori, normal, k, w_cd=1.0, w_hd=0.1, w_curv=1.0, dtype
     return dict(cd=cd.detach().numpy(), hd=hd.detach().numpy(), curv=cu.detach().numpy(),
                 kappa_ori=kap_ori.detach().numpy(), kappa_adv=kap_adv.detach().numpy(),
                 nrm_adv=nrm_adv.detach().numpy(), grad=adv_t.grad.numpy())
+
+
+class _Pointnet2Shim(object):
+    """CPU stand-in for the `pointnet2_utils` name that the reference's uniform_loss uses without importing
+    it (Lib/loss_utils.py:164-168).  Index ops come from the C oracle (restating sampling_gpu.cu /
+    ball_query_gpu.cu); the two differentiable gathers are plain torch.gather.  Argument orders are the
+    reference's Python ones (pointnet2_utils.py:37,71,197,246)."""
+
+    @staticmethod
+    def furthest_point_sample(xyz, npoint):
+        from . import oracle as O
+
+        return torch.from_numpy(O.fps(xyz.detach().float().numpy(), int(npoint)))
+
+    @staticmethod
+    def gather_operation(features, idx):
+        c = features.shape[1]
+        return features.gather(2, idx.long().unsqueeze(1).expand(-1, c, -1))
+
+    @staticmethod
+    def ball_query(radius, nsample, xyz, new_xyz):
+        from . import oracle as O
+
+        return torch.from_numpy(O.ball_query(new_xyz.detach().float().numpy(), xyz.detach().float().numpy(),
+                                             float(radius), int(nsample)))
+
+    @staticmethod
+    def grouping_operation(features, idx):
+        b, c, n = features.shape
+        _, m, ns = idx.shape
+        flat = idx.long().reshape(b, 1, m * ns).expand(-1, c, -1)
+        return features.gather(2, flat).view(b, c, m, ns)
+
+
+def aux_losses_and_grads(adv, ori, normal, k=4, dtype=torch.float32, with_uniform=True):
+    """Runs the reference's neighbourhood regularisers (Lib/loss_utils.py:99-190) verbatim and back-propagates
+    the sum of each; returns {name: value, name+'_grad': d sum(value) / d adv}.  uniform_loss gets the name it
+    forgot to import and an identity `.cuda()` (its :161) — nothing else is touched."""
+    m = load()
+    ori_t = torch.from_numpy(np.asarray(ori)).to(dtype)
+    nrm_t = torch.from_numpy(np.asarray(normal)).to(dtype)
+    calls = dict(
+        displacement=lambda a: m.displacement_loss(a, ori_t, k),
+        corr_normal=lambda a: m.corresponding_normal_loss(a, nrm_t, k),
+        repulsion=lambda a: m.repulsion_loss(a, k, 0.03),
+        kmean=lambda a: m.distance_kmean_loss(a, k),
+        smoothing=lambda a: m.kNN_smoothing_loss(a, k),
+    )
+    if with_uniform:
+        calls["uniform"] = lambda a: m.uniform_loss(a)
+    out = {}
+    m.pointnet2_utils = _Pointnet2Shim
+    saved_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **kw: self
+    try:
+        for name, fn in calls.items():
+            a = torch.from_numpy(np.asarray(adv)).to(dtype).requires_grad_(True)
+            v = fn(a)
+            v.sum().backward()
+            out[name] = v.detach().numpy()
+            out[name + "_grad"] = a.grad.numpy()
+    finally:
+        torch.Tensor.cuda = saved_cuda
+        del m.pointnet2_utils
+    return out

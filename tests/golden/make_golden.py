@@ -23,12 +23,16 @@ CASES = [
     ("loss_b2_n500_k8", 2, 500, 8, 1e-3, 3),     # ragged n, reference-sized initial perturbation
     ("loss_b4_n128_k16_big", 4, 128, 16, 1e-1, 6),  # large perturbation: many-to-one argmins, empty columns
 ]
+AUX_CASES = [
+    ("aux_b2_n512_k4", 2, 512, 4, 1e-2, 1),
+    ("aux_b3_n300_k8", 3, 300, 8, 3e-2, 5),
+]
 
 
-def main():
+def main(which=("loss", "aux")):
     torch.manual_seed(0)
     torch.set_num_threads(4)
-    for name, b, n, k, std, start in CASES:
+    for name, b, n, k, std, start in (CASES if "loss" in which else []):
         pc, nr, lab = synth.make_batch(b, n, start)
         adv = pc + synth.make_offsets(b, n, seed=7 + start, std=std)
         r32 = ref_loader.geo_loss_and_grad(adv, pc, nr, k, dtype=torch.float32)
@@ -41,6 +45,18 @@ def main():
         np.savez_compressed(osp.join(HERE, name + ".npz"), **out)
         print(name, "cd", r32["cd"], "hd", r32["hd"], "curv", r32["curv"])
 
+    # neighbourhood regularisers (Lib/loss_utils.py:99-190), same reference module, k neighbours
+    for name, b, n, k, std, start in (AUX_CASES if "aux" in which else []):
+        pc, nr, lab = synth.make_batch(b, n, start)
+        adv = pc + synth.make_offsets(b, n, seed=11 + start, std=std)
+        out = dict(adv=adv, ori=pc, normal=nr, k=np.int32(k))
+        for tag, dt in (("f32_", torch.float32), ("f64_", torch.float64)):
+            for key, v in ref_loader.aux_losses_and_grads(adv, pc, nr, k, dtype=dt).items():
+                out[tag + key] = v
+        np.savez_compressed(osp.join(HERE, name + ".npz"), **out)
+        print(name, {key: float(np.asarray(out["f32_" + key]).mean()) for key in
+                     ("displacement", "corr_normal", "repulsion", "kmean", "smoothing", "uniform")})
+
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]) or ("loss", "aux"))   # `make_golden.py aux` regenerates only the aux_* fixtures

@@ -83,3 +83,18 @@ def test_pointnetpp_attack_step_runs():
     cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=3)
     out = atk.attack(net, _data(2, 1024), cfg, use_cuda_graph=True)
     assert np.isfinite(np.asarray(out[4])).all()
+
+
+def test_attack_step_with_uniform_loss_captures():
+    """--uniform_loss_weight != 0 (geoA3_attack.py:169-171): the step still captures into a CUDA graph and the
+    replay reproduces the eager run."""
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=4, curv_loss_knn=8, uniform_loss_weight=0.5)
+    data = _data(3, 512)
+    out_g = atk.attack(net, data, cfg, use_cuda_graph=True)
+    out_e = atk.attack(net, data, cfg, use_cuda_graph=False)
+    assert np.allclose(np.asarray(out_g[4]), np.asarray(out_e[4]), rtol=1e-4, atol=1e-5)
+    cfg0 = atk.make_cfg(binary_max_steps=1, iter_max_steps=4, curv_loss_knn=8)
+    assert not np.allclose(np.asarray(out_e[4]), np.asarray(atk.attack(net, data, cfg0, use_cuda_graph=False)[4]))

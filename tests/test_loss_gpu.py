@@ -391,3 +391,46 @@ def test_api_ragged_sizes_and_small_k():
     assert rel_err(cu_.detach().cpu().numpy(), fwd["curv"]) < TOL
     Gc = O.geo_backward(adv2, pc, fwd, ko.cpu().numpy(), 0.0, 0.0, 1.0)
     assert rel_err(a2.grad.cpu().numpy(), Gc) < TOL
+
+
+def _aux_calls(L, ori, nrm, k):
+    return dict(displacement=lambda a: L.displacement_loss(a, ori, k),
+                corr_normal=lambda a: L.corresponding_normal_loss(a, nrm, k),
+                repulsion=lambda a: L.repulsion_loss(a, k, 0.03),
+                kmean=lambda a: L.distance_kmean_loss(a, k),
+                smoothing=lambda a: L.kNN_smoothing_loss(a, k),
+                uniform=lambda a: L.uniform_loss(a))
+
+
+@pytest.mark.parametrize("path", golden_files("aux_"), ids=lambda p: p.split("/")[-1])
+def test_regularisers_vs_reference_golden(path):
+    """Lib/loss_utils.py:99-190 on the CUDA neighbour searches vs the reference module's own outputs and
+    autograd gradients (fixtures from tests/golden/make_golden.py).  Values 1e-5 relative; gradients are held
+    to the accuracy the reference's own fp32 run achieves against its fp64 run (x4, floor 1e-5)."""
+    from geoa3_b200 import loss_utils as L
+
+    g = np.load(path)
+    k = int(g["k"])
+    ori, nrm = cu(g["ori"]), cu(g["normal"])
+    for name, fn in _aux_calls(L, ori, nrm, k).items():
+        a = cu(g["adv"]).requires_grad_(True)
+        v = fn(a)
+        v.sum().backward()
+        assert tuple(v.shape) == tuple(g["f32_" + name].shape), name
+        assert rel_err(v.detach().cpu().numpy(), g["f64_" + name]) < TOL, name
+        ref64 = g["f64_" + name + "_grad"]
+        bar = max(TOL, 4 * rel_err(g["f32_" + name + "_grad"], ref64))
+        assert rel_err(a.grad.cpu().numpy(), ref64) < bar, (name, bar)
+
+
+def test_regularisers_vs_oracle_seeded():
+    """Same functions at other sizes / k against the numpy restatement (values), incl. a K=33 search."""
+    from geoa3_b200 import loss_utils as L
+
+    for (b, n, k, std) in ((3, 1024, 16, 1e-2), (2, 700, 32, 5e-2), (4, 200, 2, 1e-3)):
+        adv, ori, nrm = make(b, n, 2, std)
+        want = O.aux_losses(adv, ori, nrm, k)
+        calls = _aux_calls(L, cu(ori), cu(nrm), k)
+        for name, w in want.items():
+            assert rel_err(calls[name](cu(adv)).cpu().numpy(), w) < TOL, (name, n, k)
+        assert abs(float(L.uniform_loss(cu(adv))) - O.uniform_loss(adv)) < TOL * O.uniform_loss(adv)

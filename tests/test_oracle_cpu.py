@@ -137,3 +137,15 @@ def test_three_nn_interpolate():
     go = rng.standard_normal(out.shape).astype(np.float32)
     gp = O.three_interpolate_grad(go, i, w, 23)
     assert abs((out * go).sum() - (pts * gp).sum()) < 1e-9
+
+
+@pytest.mark.parametrize("path", golden_files("aux_"), ids=lambda p: p.split("/")[-1])
+def test_oracle_regularisers_match_reference_golden(path):
+    """Lib/loss_utils.py:99-190 (displacement ... uniform): the numpy restatement on the C oracle's exact
+    neighbour lists reproduces the reference module's own fp64 outputs stored in the fixture."""
+    g = np.load(path)
+    got = O.aux_losses(g["adv"], g["ori"], g["normal"], int(g["k"]))
+    for key, v in got.items():
+        assert rel_err(v, g["f64_" + key]) < 1e-12, key
+        assert rel_err(v, g["f32_" + key]) < 1e-5, key
+    assert abs(O.uniform_loss(g["adv"]) - float(g["f64_uniform"])) < 1e-10 * float(g["f64_uniform"])
