@@ -93,7 +93,7 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------ workload
 def make_inputs(b, n, start):
-    from oracle import synth  # synthetic data generator only (numpy); not the CPU oracle
+    from geoa3_b200 import synth
 
     base = min(b, 50)
     pc, nr, lab = synth.make_batch(base, n, start)

@@ -172,3 +172,43 @@ def aux_losses_and_grads(adv, ori, normal, k=4, dtype=torch.float32, with_unifor
         torch.Tensor.cuda = saved_cuda
         del m.pointnet2_utils
     return out
+
+
+_defense = None
+
+
+def load_defense():
+    """The reference's defense.py module object (functions only; its CLI lives under __main__).  Its
+    `Lib.utility` import (seaborn / matplotlib / tty) is stubbed — none of the three removal functions uses it."""
+    global _defense
+    if _defense is not None:
+        return _defense
+    import torch.autograd.gradcheck  # noqa: F401
+
+    sys.modules["torch.autograd.gradcheck"].zero_gradients = lambda *a, **k: None
+    saved = {k: sys.modules.get(k) for k in ("Lib", "Lib.utility")}
+    lib, util = types.ModuleType("Lib"), types.ModuleType("Lib.utility")
+    util.farthest_points_sample = None
+    lib.utility = util
+    sys.modules["Lib"], sys.modules["Lib.utility"] = lib, util
+    spec = importlib.util.spec_from_file_location("ref_defense", osp.join(REF_ROOT, "defense.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)
+    _defense = mod
+    return mod
+
+
+def defense_outputs(pc, drop_num, alpha, outlier_knn):
+    """Runs the reference's two statistical filters on ONE cloud pc [1,3,n] (CPU); returns kept clouds + counts."""
+    d = load_defense()
+    t = torch.from_numpy(np.asarray(pc, np.float32))
+    var_pc, var_num = d.outlier_removal_fn(t, "outliers_variance", drop_num, alpha, outlier_knn)
+    fix_pc, fix_num = d.outlier_removal_fn(t, "outliers_fixNum", drop_num, alpha, outlier_knn)
+    return dict(var_pc=var_pc.numpy(), var_num=np.int64(var_num), fix_pc=fix_pc.numpy(), fix_num=np.int64(fix_num))

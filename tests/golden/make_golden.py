@@ -23,13 +23,18 @@ CASES = [
     ("loss_b2_n500_k8", 2, 500, 8, 1e-3, 3),     # ragged n, reference-sized initial perturbation
     ("loss_b4_n128_k16_big", 4, 128, 16, 1e-1, 6),  # large perturbation: many-to-one argmins, empty columns
 ]
+DEFENSE_CASES = [  # n, outlier_knn, alpha, drop_num, offset std
+    (1024, 2, 1.1, 50, 1e-2),
+    (700, 8, 0.5, 123, 3e-2),
+    (333, 16, 2.0, 1, 1e-3),
+]
 AUX_CASES = [
     ("aux_b2_n512_k4", 2, 512, 4, 1e-2, 1),
     ("aux_b3_n300_k8", 3, 300, 8, 3e-2, 5),
 ]
 
 
-def main(which=("loss", "aux")):
+def main(which=("loss", "aux", "defense")):
     torch.manual_seed(0)
     torch.set_num_threads(4)
     for name, b, n, k, std, start in (CASES if "loss" in which else []):
@@ -57,6 +62,20 @@ def main(which=("loss", "aux")):
         print(name, {key: float(np.asarray(out["f32_" + key]).mean()) for key in
                      ("displacement", "corr_normal", "repulsion", "kmean", "smoothing", "uniform")})
 
+    # defense.py statistical outlier filters (:25-40) on adversarially perturbed single clouds with planted outliers
+    if "defense" in which:
+        out = {}
+        for i, (n, knn, alpha, drop, std) in enumerate(DEFENSE_CASES):
+            pc, _, _ = synth.make_batch(1, n, i)
+            adv = pc + synth.make_offsets(1, n, seed=21 + i, std=std)
+            adv[0, :, ::37] += synth.make_offsets(1, n, seed=31 + i, std=0.15)[0, :, ::37]   # a few far outliers
+            out["c%d_pc" % i] = adv.astype(np.float32)
+            out["c%d_args" % i] = np.array([drop, alpha, knn], np.float64)
+            for key, v in ref_loader.defense_outputs(adv, drop, alpha, knn).items():
+                out["c%d_%s" % (i, key)] = v
+            print("defense case", i, "removed", out["c%d_var_num" % i], out["c%d_fix_num" % i])
+        np.savez_compressed(osp.join(HERE, "defense_cases.npz"), **out)
+
 
 if __name__ == "__main__":
-    main(tuple(sys.argv[1:]) or ("loss", "aux"))   # `make_golden.py aux` regenerates only the aux_* fixtures
+    main(tuple(sys.argv[1:]) or ("loss", "aux", "defense"))   # e.g. `make_golden.py aux` regenerates only aux_*

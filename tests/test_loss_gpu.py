@@ -434,3 +434,26 @@ def test_regularisers_vs_oracle_seeded():
         for name, w in want.items():
             assert rel_err(calls[name](cu(adv)).cpu().numpy(), w) < TOL, (name, n, k)
         assert abs(float(L.uniform_loss(cu(adv))) - O.uniform_loss(adv)) < TOL * O.uniform_loss(adv)
+
+
+def test_defense_filters_vs_reference_golden():
+    """defense.py:25-40 (statistical outlier removal) on the CUDA top-K search vs the reference's own function
+    outputs: the same points are kept (bit-identical kept clouds), the same counts are returned."""
+    import os.path as osp
+
+    from geoa3_b200 import defense as D
+    from helpers import GOLDEN_DIR
+
+    g = np.load(osp.join(GOLDEN_DIR, "defense_cases.npz"))
+    i = 0
+    while "c%d_pc" % i in g:
+        pc = cu(g["c%d_pc" % i])
+        drop, alpha, knn = g["c%d_args" % i]
+        out, num = D.point_removal_fn(pc, "outliers_variance", int(drop), float(alpha), int(knn))
+        assert num == int(g["c%d_var_num" % i]) and np.array_equal(out.cpu().numpy(), g["c%d_var_pc" % i])
+        out, num = D.point_removal_fn(pc, "outliers_fixNum", int(drop), float(alpha), int(knn))
+        assert num == int(g["c%d_fix_num" % i]) and np.array_equal(out.cpu().numpy(), g["c%d_fix_pc" % i])
+        out, num = D.point_removal_fn(pc, "rand_drop", int(drop), float(alpha), int(knn))
+        assert num == int(drop) and out.shape == (1, 3, pc.shape[2] - int(drop))
+        i += 1
+    assert i == 3

@@ -1,7 +1,7 @@
 import sys, numpy as np, torch
 sys.path.insert(0,'/root/repo')
 from geoa3_b200 import ops
-from oracle import synth
+from geoa3_b200 import synth
 from tools.time_kernels import timeit
 b,n,k=250,1024,16
 pc,nr,_=synth.make_batch(20,n)

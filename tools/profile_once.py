@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
 from geoa3_b200 import ops  # noqa: E402
-from oracle import synth  # noqa: E402
+from geoa3_b200 import synth  # noqa: E402
 
 b, n, k = 250, 1024, 16
 pc, nr, _ = synth.make_batch(10, n)

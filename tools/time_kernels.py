@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
 from geoa3_b200 import ops  # noqa: E402
-from oracle import synth  # noqa: E402
+from geoa3_b200 import synth  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=5, flush=None):
