@@ -176,6 +176,87 @@ fps_warp_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref
   }
 }
 
+// Four-warp variant for n <= 2048 (P = 2..16 points per lane).  ubench/fps_probe.cu shows that a round of the
+// single-warp kernel is a ~600-cycle LATENCY chain (distance/min/max 290, tie-break search 200, REDUX + store 80,
+// LDS 37) that barely shrinks with fewer points per lane, i.e. one warp cannot hide its own dependent chains.
+// Here a cloud is spread over the 4 schedulers of an SM (P/4 as many points per lane => short chains), the
+// per-lane tie-break key is computed unconditionally next to the first REDUX instead of after it (no divergent
+// search), and the 4 warp partials are merged through a double-buffered shared slot with ONE barrier per round.
+constexpr int FPSQ_WARPS = 4;
+
+template <int P>
+__global__ void __launch_bounds__(FPSQ_WARPS * 32)
+fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs) {
+  static_assert(P % 2 == 0, "points are packed in pairs");
+  extern __shared__ __align__(16) float s_xyz[];  // [3][n] SoA mirror (broadcast of the last pick), then int s_out[m]
+  __shared__ __align__(16) unsigned long long s_part[2][FPSQ_WARPS];
+  // picks are collected in shared memory and written out once: a global store per round sits in front of the
+  // next round's block barrier (which orders global accesses too) and costs ~100 cycles per round (fps_probe)
+  int* s_out = reinterpret_cast<int*>(s_xyz + 3 * n);
+  constexpr int T = FPSQ_WARPS * 32, H = P / 2;
+  const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* p = xyz + (size_t)cloud * n * 3;
+  int32_t* out = idxs + (size_t)cloud * m;
+  float2 px[H], py[H], pz[H], temp[H];
+  unsigned tk[P];
+#pragma unroll
+  for (int t = 0; t < P; ++t) {
+    const int k = tid + t * T;
+    float x = 0.f, y = 0.f, z = 0.f, t0 = 0.f;
+    tk[t] = 0u;
+    if (k < n) {
+      x = p[k * 3]; y = p[k * 3 + 1]; z = p[k * 3 + 2];
+      s_xyz[k] = x; s_xyz[n + k] = y; s_xyz[2 * n + k] = z;
+      const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+      const unsigned rtid = ref_bits ? (__brev((unsigned)(k % ref_bs)) >> (32 - ref_bits)) : 0u;
+      if (!((double)mag <= 1e-3)) { tk[t] = ~((rtid << 20) | (unsigned)k); t0 = 1e10f; }  // else frozen: temp 0, key 0
+    }
+    if (t & 1) { px[t >> 1].y = x; py[t >> 1].y = y; pz[t >> 1].y = z; temp[t >> 1].y = t0; }
+    else { px[t >> 1].x = x; py[t >> 1].x = y; pz[t >> 1].x = z; temp[t >> 1].x = t0; }
+  }
+  if (tid == 0) s_out[0] = 0;
+  __syncthreads();
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = -s_xyz[old], y1 = -s_xyz[n + old], z1 = -s_xyz[2 * n + old];
+    const float2 nx = make_float2(x1, x1), ny = make_float2(y1, y1), nz = make_float2(z1, z1);
+    float hm[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float2 d = dist2x2_pn2(px[h], py[h], pz[h], nx, ny, nz);
+      temp[h].x = fminf(d.x, temp[h].x);  // frozen / padding points sit at 0 forever
+      temp[h].y = fminf(d.y, temp[h].y);
+      hm[h] = fmaxf(temp[h].x, temp[h].y);
+    }
+#pragma unroll
+    for (int st = 1; st < H; st <<= 1)
+#pragma unroll
+      for (int h = 0; h + st < H; h += 2 * st) hm[h] = fmaxf(hm[h], hm[h + st]);
+    const float hmax = hm[0];
+    const unsigned gw = __reduce_max_sync(0xffffffffu, __float_as_uint(hmax));  // distances >= +0: bit order
+    // this lane's best tie-break key among its points at hmax — independent of the REDUX above
+    unsigned kk[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+      kk[h] = max(temp[h].x == hmax ? tk[2 * h] : 0u, temp[h].y == hmax ? tk[2 * h + 1] : 0u);
+#pragma unroll
+    for (int st = 1; st < H; st <<= 1)
+#pragma unroll
+      for (int h = 0; h + st < H; h += 2 * st) kk[h] = max(kk[h], kk[h + st]);
+    const unsigned lw = __reduce_max_sync(0xffffffffu, __float_as_uint(hmax) == gw ? kk[0] : 0u);
+    if (lane == 0) s_part[j & 1][w] = ((unsigned long long)gw << 32) | lw;
+    __syncthreads();
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&s_part[j & 1][0]);
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&s_part[j & 1][2]);
+    const unsigned long long ab = a.x > a.y ? a.x : a.y, cd = b.x > b.y ? b.x : b.y;
+    const unsigned lo = (unsigned)(ab > cd ? ab : cd);
+    old = lo != 0u ? (int)((~lo) & 0xFFFFFu) : 0;
+    if (tid == 0) s_out[j] = old;
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += T) out[i] = s_out[i];
+}
+
 // ============================================================================ ball query
 constexpr int BQ_WARPS = 8;
 constexpr int BQ_PER_WARP = 8;  // centroids handled sequentially by one warp
@@ -225,6 +306,85 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
     int32_t* o = idx + ((size_t)cloud * m + c) * nsample;
     for (int l = lane; l < nsample; l += 32) o[l] = l < cnt ? row[l] : first;
     __syncwarp();
+  }
+}
+
+// ---- thread-per-centroid variant (n <= 65535).  The warp-per-centroid kernel above pays a ballot + prefix per 64
+// candidates; balls are small (typically ~1 % of the cloud), so almost every candidate is a miss and the cheap
+// thing is the knn inner loop: one thread = one centroid, candidates broadcast from shared memory as float4,
+// packed distance, pass bit = sign of (d - r^2) shifted into a 32-candidate mask.  Hits (rare) go to a per-thread
+// shared row in scan order; rows are written out coalesced with the first-hit padding.
+constexpr int BQT_THREADS = 128;
+constexpr int BQT_CHUNK = 1024;
+
+__global__ void __launch_bounds__(BQT_THREADS)
+ball_query_thread_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int n, int m, float radius,
+                         int nsample, int32_t* __restrict__ idx) {
+  __shared__ __align__(16) float sx[BQT_CHUNK];
+  __shared__ __align__(16) float sy[BQT_CHUNK];
+  __shared__ __align__(16) float sz[BQT_CHUNK];
+  extern __shared__ uint16_t s_hits[];  // [BQT_THREADS][pitch], pitch = nsample + 2 (skews the banks)
+  const int cloud = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int c = blockIdx.x * BQT_THREADS + tid;
+  const int pitch = nsample + 2;
+  const float* q = new_xyz + ((size_t)cloud * m + min(c, m - 1)) * 3;
+  const float qx = -q[0], qy = -q[1], qz = -q[2];
+  const float2 nqx = make_float2(qx, qx), nqy = make_float2(qy, qy), nqz = make_float2(qz, qz);
+  const float r2 = __fmul_rn(radius, radius);
+  const float2 nr2 = make_float2(-r2, -r2);
+  const float* p = xyz + (size_t)cloud * n * 3;
+  uint16_t* mine = s_hits + (size_t)tid * pitch;
+  int cnt = c < m ? 0 : nsample;  // threads past the last centroid count as full
+  for (int c0 = 0; c0 < n; c0 += BQT_CHUNK) {
+    const int cn = min(BQT_CHUNK, n - c0), cn32 = (cn + 31) & ~31;
+    __syncthreads();
+    for (int i = tid; i < cn32; i += BQT_THREADS) {
+      const bool ok = i < cn;
+      sx[i] = ok ? p[(size_t)(c0 + i) * 3] : __int_as_float(0x7f800000);  // padding is never inside a ball
+      sy[i] = ok ? p[(size_t)(c0 + i) * 3 + 1] : 0.f;
+      sz[i] = ok ? p[(size_t)(c0 + i) * 3 + 2] : 0.f;
+    }
+    __syncthreads();
+    for (int j = 0; j < cn32; j += 32) {
+      if (__all_sync(0xffffffffu, cnt >= nsample)) break;
+      unsigned mask = 0u;
+#pragma unroll 2
+      for (int u = 0; u < 32; u += 8) {
+        const float4 cxa = *reinterpret_cast<const float4*>(sx + j + u), cxb = *reinterpret_cast<const float4*>(sx + j + u + 4);
+        const float4 cya = *reinterpret_cast<const float4*>(sy + j + u), cyb = *reinterpret_cast<const float4*>(sy + j + u + 4);
+        const float4 cza = *reinterpret_cast<const float4*>(sz + j + u), czb = *reinterpret_cast<const float4*>(sz + j + u + 4);
+        // d < r2  <=>  d - r2 < 0 exactly (a float difference is zero only for equal operands; no flush-to-zero)
+        const float2 s01 = __fadd2_rn(dist2x2_pn2(make_float2(cxa.x, cxa.y), make_float2(cya.x, cya.y), make_float2(cza.x, cza.y), nqx, nqy, nqz), nr2);
+        const float2 s23 = __fadd2_rn(dist2x2_pn2(make_float2(cxa.z, cxa.w), make_float2(cya.z, cya.w), make_float2(cza.z, cza.w), nqx, nqy, nqz), nr2);
+        const float2 s45 = __fadd2_rn(dist2x2_pn2(make_float2(cxb.x, cxb.y), make_float2(cyb.x, cyb.y), make_float2(czb.x, czb.y), nqx, nqy, nqz), nr2);
+        const float2 s67 = __fadd2_rn(dist2x2_pn2(make_float2(cxb.z, cxb.w), make_float2(cyb.z, cyb.w), make_float2(czb.z, czb.w), nqx, nqy, nqz), nr2);
+        mask = __funnelshift_l(__float_as_uint(s01.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s01.y), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s23.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s23.y), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s45.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s45.y), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s67.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(s67.y), mask, 1);
+      }
+      while (mask && cnt < nsample) {  // bit 31 is candidate j: ascending index = descending bit
+        const int t = __clz(mask);
+        mask &= ~(0x80000000u >> t);
+        mine[cnt++] = (uint16_t)(c0 + j + t);
+      }
+    }
+  }
+  __syncwarp();
+  // rows of this warp's 32 centroids, one coalesced row at a time; first-hit fill, an empty ball keeps zeros
+  const int wbase = tid & ~31;
+  for (int r = 0; r < 32; ++r) {
+    const int cr = blockIdx.x * BQT_THREADS + wbase + r;
+    if (cr >= m) break;
+    const int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
+    const uint16_t* row = s_hits + (size_t)(wbase + r) * pitch;
+    const int first = cnt_r > 0 ? (int)row[0] : 0;
+    int32_t* o = idx + ((size_t)cloud * m + cr) * nsample;
+    for (int l = lane; l < nsample; l += 32) o[l] = l < cnt_r ? (int)row[l] : first;
   }
 }
 
@@ -850,10 +1010,19 @@ extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  if (n <= 512) {
+  const bool one_warp = getenv("GEOA3_FPS_WARP") != nullptr;  // A/B knob for tools/time_kernels.py, not part of the API
+  if (one_warp && n <= 512) {
     fps_warp_kernel<16><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
-  } else if (n <= 1024) {
+  } else if (one_warp && n <= 1024) {
     fps_warp_kernel<32><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 256) {
+    fps_quad_kernel<2><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 512) {
+    fps_quad_kernel<4><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 1024) {
+    fps_quad_kernel<8><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 2048) {
+    fps_quad_kernel<16><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
   } else if (n <= 4096) {
     const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
     fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx);
@@ -878,6 +1047,19 @@ extern "C" int geoa3_ball_query(const float* new_xyz, const float* xyz, int b, i
     cudaError_t e = cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
+  }
+  if (n <= 65535 && !getenv("GEOA3_BQ_WARP")) {  // (env: A/B knob for tools/time_kernels.py, not part of the API)
+    const size_t hs = (size_t)BQT_THREADS * (nsample + 2) * sizeof(uint16_t);
+    static bool attr_t = false;
+    if (!attr_t) {
+      cudaError_t e = cudaFuncSetAttribute(ball_query_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           BQT_THREADS * (BQ_MAX_NS + 2) * (int)sizeof(uint16_t));
+      if (e != cudaSuccess) return (int)e;
+      attr_t = true;
+    }
+    ball_query_thread_kernel<<<dim3(ceil_div(m, BQT_THREADS), b), BQT_THREADS, hs, (cudaStream_t)stream>>>(
+        new_xyz, xyz, n, m, radius, nsample, idx);
+    return GEOA3_LAUNCH_RESULT();
   }
   dim3 grid(ceil_div(m, BQ_WARPS * BQ_PER_WARP), b);
   ball_query_kernel<<<grid, BQ_WARPS * 32, smem, (cudaStream_t)stream>>>(new_xyz, xyz, n, m, radius, nsample, idx);
