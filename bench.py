@@ -139,7 +139,7 @@ def kernel_breakdown(pc_ori, nrm, adv, k):
     prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
     _, hj, _, hi = ops.nn_pair(prev, pc_ori)
     hn = ops.knn(prev, prev, k + 1, drop=1)[0]
-    perm, iperm = ops.morton_order(pc_ori)  # once per attack in the real driver (HintBuffers.ensure_order)
+    perm, iperm = ops.visit_order(pc_ori)  # once per attack in the real driver (HintBuffers.ensure_order)
     nnkw = dict(hint_a2o=hj, hint_o2a=hi, perm_a=perm, perm_o=perm, iperm_a=iperm, iperm_o=iperm,
                 ori_arranged=ops.arrange(pc_ori, perm))
     d1, js, d2, is_ = ops.nn_pair(adv, pc_ori, **nnkw)
@@ -154,7 +154,7 @@ def kernel_breakdown(pc_ori, nrm, adv, k):
     out = fwd()
     g = torch.full((b,), 1.0 / b, device=adv.device)
     t = {
-        "nn_pair": time_events(lambda: ops.nn_pair(adv, pc_ori, **nnkw), 10, 3),  # incl. the gather arranging adv
+        "nn_pair": time_events(lambda: ops.nn_pair(adv, pc_ori, **nnkw), 10, 3),  # incl. the launch arranging adv
         "knn": time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), 10, 3),
         "kappa_loss_fwd": time_events(fwd, 10, 3),
         "loss_bwd": time_events(lambda: ops.loss_bwd(adv, ori=pc_ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"],

@@ -21,6 +21,7 @@ SIGNATURES = {
     "geoa3_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "geoa3_group_bbox_floats": (_sz, [_i]),
     "geoa3_group_bbox": (_i, [_vp, _i, _i, _vp, _vp]),
+    "geoa3_arrange": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "geoa3_kappa_loss_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geoa3_loss_bwd": (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp, _vp]),
     "geoa3_furthest_point_sampling": (_i, [_vp, _i, _i, _i, _vp, _vp]),

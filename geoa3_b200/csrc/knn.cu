@@ -259,11 +259,14 @@ static int launch_knn(const float* query, const float* ref, int b, int n, int m,
 
 // Bounding boxes of an arranged cloud: level 0 = every 32 consecutive positions, level 1 = every KNN_CHUNK.
 // bb layout per cloud: [G0 + G1][8] floats = lo xyz, hi xyz, max |p|^2, pad.
-__global__ void group_bbox_kernel(const float* __restrict__ pc, int n, float* __restrict__ bb) {
+// With `perm` the cloud is first ARRANGED (position t takes original point perm[t]) and written to `arranged`:
+// one launch replaces the gather + box pass of every pruned search of a step.
+__global__ void group_bbox_kernel(const float* __restrict__ pc, const int32_t* __restrict__ perm,
+                                  float* __restrict__ arranged, int n, float* __restrict__ bb) {
   const int cloud = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int G0 = (n + 31) >> 5, G1 = (n + KNN_CHUNK - 1) / KNN_CHUNK;
   const float* p = pc + (size_t)cloud * 3 * n;
-  float* out = bb + (size_t)cloud * (G0 + G1) * 8;
+  float* out = bb ? bb + (size_t)cloud * (G0 + G1) * 8 : nullptr;
   const int per = KNN_CHUNK / 32;                 // level-0 groups per level-1 box; one CTA (32 warps) per level-1 box
   const int g1 = blockIdx.x;
   __shared__ float s_box[32][8];
@@ -271,9 +274,15 @@ __global__ void group_bbox_kernel(const float* __restrict__ pc, int n, float* __
   const int g = g1 * per + wib;
   const int t = g * 32 + lane;
   if (g < G0 && t < n) {
-    const float x = p[t], y = p[n + t], z = p[2 * n + t];
+    const int src = perm ? perm[(size_t)cloud * n + t] : t;
+    const float x = p[src], y = p[n + src], z = p[2 * n + src];
+    if (arranged) {
+      float* a = arranged + (size_t)cloud * 3 * n;
+      a[t] = x; a[n + t] = y; a[2 * n + t] = z;
+    }
     lx = hx = x; ly = hy = y; lz = hz = z; w2 = x * x + y * y + z * z;
   }
+  if (!out) return;  // arrangement only (uniform per launch)
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, s)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, s));
@@ -316,7 +325,18 @@ extern "C" int geoa3_group_bbox(const float* pc_arranged, int b, int n, float* b
   GEOA3_CHECK_ARG(pc_arranged && bb && b > 0 && n > 0);
   if (b > 65535) return GEOA3_EUNSUPPORTED;
   static_assert(KNN_CHUNK == 1024, "one 1024-thread CTA per level-1 box");
-  group_bbox_kernel<<<dim3((n + KNN_CHUNK - 1) / KNN_CHUNK, b), 1024, 0, (cudaStream_t)stream>>>(pc_arranged, n, bb);
+  group_bbox_kernel<<<dim3((n + KNN_CHUNK - 1) / KNN_CHUNK, b), 1024, 0, (cudaStream_t)stream>>>(pc_arranged, nullptr,
+                                                                                               nullptr, n, bb);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_arrange(const float* pc, const int32_t* perm, int b, int n, float* arranged, float* bb,
+                             geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(pc && perm && arranged && pc != arranged && b > 0 && n > 0);
+  if (b > 65535) return GEOA3_EUNSUPPORTED;
+  group_bbox_kernel<<<dim3((n + KNN_CHUNK - 1) / KNN_CHUNK, b), 1024, 0, (cudaStream_t)stream>>>(pc, perm, arranged, n,
+                                                                                               bb);
   return GEOA3_LAUNCH_RESULT();
 }
 

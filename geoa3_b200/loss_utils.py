@@ -59,13 +59,13 @@ class HintBuffers(object):
     def __init__(self, prune_min_n_knn=2048):
         self.d1 = self.jstar = self.d2 = self.istar = None
         self.nbr = {}
-        # visiting order for the pruned searches: Morton order of the ORIGINAL cloud, computed once (first call)
+        # visiting order for the pruned searches (ops.visit_order of the ORIGINAL cloud), computed once (first call)
         self.perm = self.iperm = self.ori_arranged = None
         self.prune_min_n_knn = prune_min_n_knn  # measured: box pruning of the kNN scan only pays for larger clouds
 
     def ensure_order(self, ori):
         if self.perm is None or self.perm.shape != (ori.shape[0], ori.shape[2]):
-            self.perm, self.iperm = ops.morton_order(ori)
+            self.perm, self.iperm = ops.visit_order(ori)
             self.ori_arranged = ops.arrange(ori, self.perm)
 
     def ensure_nn(self, b, n, m, dev):
@@ -77,7 +77,7 @@ class HintBuffers(object):
 
 
 _LAST = {}  # (device, b, n, m) -> last results, reused as (non-aliased) hints by the plain reference API
-_ORDER = {}  # id(ori) -> (weakref(ori), version, perm, iperm, ori_arranged): Morton order of a cloud seen before
+_ORDER = {}  # id(ori) -> (weakref(ori), version, perm, iperm, ori_arranged): visiting order of a cloud seen before
 
 
 def _order_of(ori_obj, ori_c):
@@ -86,7 +86,7 @@ def _order_of(ori_obj, ori_c):
     ent = _ORDER.get(id(ori_obj))
     if ent is not None and ent[0]() is ori_obj and ent[1] == ori_obj._version:
         return ent[2], ent[3], ent[4]
-    perm, iperm = ops.morton_order(ori_c)
+    perm, iperm = ops.visit_order(ori_c)
     arranged = ops.arrange(ori_c, perm)
     if len(_ORDER) > 8:
         _ORDER.clear()

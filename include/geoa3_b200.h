@@ -91,6 +91,13 @@ GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int 
 GEOA3_API size_t geoa3_group_bbox_floats(int n);
 GEOA3_API int geoa3_group_bbox(const float *pc_arranged, int b, int n, float *bb, geoa3_stream_t stream);
 
+/* Arranges a cloud in visiting order and (bb != NULL) boxes it in the same launch:
+ * arranged[b][3][n] with position t = original point perm[t]; bb as for geoa3_group_bbox.  Replaces the
+ * host-side index_select the reference would use for a permuted cloud (no counterpart in the reference: its
+ * searches are unordered brute force, Lib/loss_utils.py:32-33,57,77). */
+GEOA3_API int geoa3_arrange(const float *pc, const int32_t *perm, int b, int n, float *arranged, float *bb,
+                            geoa3_stream_t stream);
+
 /* Local curvature + per-cloud loss reductions, one CTA per cloud, fixed-order reductions.
  *   kappa_i = (1/k) sum_m |<nrm_i, v_im/max(|v_im|,1e-12)>|,  v_im = pc[nbr[i][m]] - pc[i]
  *   nrm_i   = normal[:, jstar[i]]  (jstar != NULL: _get_kappa_adv)  or normal[:, i] (jstar NULL: _get_kappa_ori)

@@ -82,10 +82,10 @@ def main():
     res["nn_pair"] = timeit(lambda: ops.nn_pair(adv, ori), flush=flush)
     d1, js, d2, is_ = ops.nn_pair(adv, ori)
     res["nn_pair_hinted"] = timeit(lambda: ops.nn_pair(adv, ori, hint_a2o=js, hint_o2a=is_), flush=flush)
-    perm, iperm = ops.morton_order(ori)
+    perm, iperm = ops.visit_order(ori)
     ori_s = ops.arrange(ori, perm)
     mk = dict(hint_a2o=js, hint_o2a=is_, perm_a=perm, perm_o=perm, iperm_a=iperm, iperm_o=iperm, ori_arranged=ori_s)
-    res["nn_pair_morton(incl. gather of adv)"] = timeit(lambda: ops.nn_pair(adv, ori, **mk), flush=flush)
+    res["nn_pair_ordered(incl. arrange of adv)"] = timeit(lambda: ops.nn_pair(adv, ori, **mk), flush=flush)
     chk = ops.nn_pair(adv, ori, **mk)
     assert torch.equal(chk[1], js) and torch.equal(chk[3], is_) and torch.equal(chk[0], d1)
     perm, iperm = ops.morton_order(ori)
@@ -110,7 +110,7 @@ def main():
     res["loss_bwd"] = timeit(lambda: ops.loss_bwd(adv, ori=ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=ko,
                                                   jstar=js, istar=is_, nbr=nbr, hd_arg=out["hd_arg"], g_cd=g, g_hd=g,
                                                   g_cu=g), flush=flush)
-    tot = res["nn_pair_hinted"][0] + res["knn_self_hinted"][0] + res["kappa_loss_fwd"][0] + res["loss_bwd"][0]
+    tot = res["nn_pair_ordered(incl. arrange of adv)"][0] + res["knn_self_hinted"][0] + res["kappa_loss_fwd"][0] + res["loss_bwd"][0]
     pairs = b * n * n
     print(json.dumps(dict(what="loss_path", b=b, n=n, k=k, us_median={k_: round(v[0], 2) for k_, v in res.items()},
                           us_min={k_: round(v[1], 2) for k_, v in res.items()}, total_us=round(tot, 2),
