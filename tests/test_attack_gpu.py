@@ -98,3 +98,37 @@ def test_attack_step_with_uniform_loss_captures():
     assert np.allclose(np.asarray(out_g[4]), np.asarray(out_e[4]), rtol=1e-4, atol=1e-5)
     cfg0 = atk.make_cfg(binary_max_steps=1, iter_max_steps=4, curv_loss_knn=8)
     assert not np.allclose(np.asarray(out_e[4]), np.asarray(atk.attack(net, data, cfg0, use_cuda_graph=False)[4]))
+
+
+def test_attack_trajectory_matches_cpu_port():
+    """Several full attack iterations (victim forward, CE + CD + 0.1 HD + curvature, backward, Adam) on the GPU
+    driver vs the dense CPU port of the reference step (oracle/torch_port.py, pinned against the reference's loss
+    functions by tests/test_port_cpu.py): same weights, same initial offsets => the per-instance loss trajectory
+    agrees.  TF32 is switched off for the victim so that the comparison is fp32 against fp32."""
+    from geoa3_b200 import attack as atk
+    from oracle import torch_port as P
+
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net = _net()
+        b, n, k, steps = 3, 256, 8, 6
+        pc, nr, lab = synth.make_batch(b, n, 0)
+        cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=steps, curv_loss_knn=k)
+        dev = torch.device("cuda")
+        pc_t, nr_t, lab_t = torch.from_numpy(pc).to(dev), torch.from_numpy(nr).to(dev), torch.from_numpy(lab).to(dev)
+        st = atk.AttackState(net, pc_t, nr_t, lab_t, lab_t, cfg, targeted=False, global_batch=b)
+        st.begin_search_step(0, atk.default_offsets(b, n, 0, 0).to(dev))
+        for _ in range(steps):
+            st.run_step()
+        got = st.loss_log[:steps].cpu().numpy()
+
+        import copy
+        cpu_net = copy.deepcopy(net).cpu().eval()
+        ref = P.CpuAttackStep(cpu_net, torch.from_numpy(pc), torch.from_numpy(nr), torch.from_numpy(lab), k=k, seed=0)
+        want = np.stack([ref.step(True).numpy() for _ in range(steps)])
+        assert np.allclose(got[0], want[0], rtol=2e-5, atol=1e-6)          # first step: pure forward parity
+        assert np.allclose(got, want, rtol=2e-3, atol=1e-4), np.abs(got - want).max()   # Adam amplifies rounding
+        assert np.abs(got[-1] - got[0]).max() > 1e-3                         # the optimisation actually moved
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
