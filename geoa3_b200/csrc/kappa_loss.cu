@@ -7,6 +7,8 @@
 //             CSR-by-target list is built in shared memory (integer shared atomics hand out the slots,
 //             then every target sorts its short segment by source id — csr.cuh), so every target sums
 //             its contributions in ascending source order — no float atomics, bitwise reproducible.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "csr.cuh"
 
@@ -279,6 +281,123 @@ static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdL
   return L->total <= budget;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Large clouds (n*k > 65535 edges, or a shared-memory plan that does not fit): the same gather with the two
+// CSRs and the per-point float4 arrays in a caller-provided GLOBAL workspace.  Same summation order as the fused
+// kernel (own terms, then incoming edges by ascending source), so the results are bit-identical to it.
+// Workspace per cloud (ints/floats, 16-byte aligned): P[n] float4 (a_i, gk_i), N[n] float4 (borrowed normal),
+// offs1[n+1], ent1[n*k], offs2[n+1], ent2[m].
+constexpr int BWL_THREADS = 512;
+
+struct BwdLargeLayout { size_t P, N, offs1, ent1, offs2, ent2, per_cloud; };  // offsets in 4-byte words
+
+static BwdLargeLayout plan_bwd_large(int n, int m, int k) {
+  BwdLargeLayout L;
+  size_t o = 0;
+  auto take = [&](size_t words) { size_t r = o; o += (words + 3) & ~(size_t)3; return r; };
+  L.P = take((size_t)4 * n); L.N = take((size_t)4 * n);
+  L.offs1 = take((size_t)n + 1); L.ent1 = take((size_t)n * (k > 0 ? k : 0));
+  L.offs2 = take((size_t)n + 1); L.ent2 = take((size_t)m);
+  L.per_cloud = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(BWL_THREADS)
+bwd_large_csr_kernel(const int32_t* __restrict__ keys, int E, int n, int W, float* __restrict__ ws, size_t per_cloud,
+                     size_t off_offs, size_t off_ent) {
+  extern __shared__ __align__(16) int s_whist_l[];
+  __shared__ int scan_scratch[BWL_THREADS / 32 + 1];
+  int* base = reinterpret_cast<int*>(ws + (size_t)blockIdx.x * per_cloud);
+  build_csr<BWL_THREADS, int, int>(keys + (size_t)blockIdx.x * E, E, n, 0u, base + off_offs, s_whist_l, W,
+                                   base + off_ent, scan_scratch);
+}
+
+__global__ void bwd_large_pack_kernel(const float* __restrict__ adv, const float* __restrict__ nrm_adv,
+                                      const float* __restrict__ kappa_adv, const float* __restrict__ kappa_ori,
+                                      const int32_t* __restrict__ jstar, const float* __restrict__ g_cu,
+                                      const float* __restrict__ g_kappa, int n, int m, bool do_curv,
+                                      float* __restrict__ ws, BwdLargeLayout L) {
+  const int cloud = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t gi = (size_t)cloud * n + i;
+  const float* a = adv + (size_t)cloud * 3 * n;
+  float4* P = reinterpret_cast<float4*>(ws + (size_t)cloud * L.per_cloud + L.P);
+  float4* N = reinterpret_cast<float4*>(ws + (size_t)cloud * L.per_cloud + L.N);
+  float gk = 0.f;
+  if (do_curv) {
+    if (g_cu) gk = g_cu[cloud] * (2.f / (float)n) * (kappa_adv[gi] - kappa_ori[(size_t)cloud * m + jstar[gi]]);
+    if (g_kappa) gk += g_kappa[gi];
+    const float* nn = nrm_adv + (size_t)cloud * 3 * n;
+    N[i] = make_float4(nn[i], nn[n + i], nn[2 * n + i], 0.f);
+  }
+  P[i] = make_float4(a[i], a[n + i], a[2 * n + i], gk);
+}
+
+__global__ void bwd_large_gather_kernel(const float* __restrict__ ori, const int32_t* __restrict__ jstar,
+                                        const int32_t* __restrict__ nbr, const int32_t* __restrict__ hd_arg,
+                                        const float* __restrict__ g_cd, const float* __restrict__ g_hd, int n, int m,
+                                        int k, bool do_curv, bool do_col, const float* __restrict__ ws,
+                                        BwdLargeLayout L, float* __restrict__ grad_adv) {
+  const int cloud = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float* base = ws + (size_t)cloud * L.per_cloud;
+  const float4* P = reinterpret_cast<const float4*>(base + L.P);
+  const float4* N = reinterpret_cast<const float4*>(base + L.N);
+  const int* offs1 = reinterpret_cast<const int*>(base + L.offs1);
+  const int* ent1 = reinterpret_cast<const int*>(base + L.ent1);
+  const int* offs2 = reinterpret_cast<const int*>(base + L.offs2);
+  const int* ent2 = reinterpret_cast<const int*>(base + L.ent2);
+  const float* o = ori ? ori + (size_t)cloud * 3 * m : nullptr;
+  const float gcd = g_cd ? g_cd[cloud] : 0.f, ghd = g_hd ? g_hd[cloud] : 0.f;
+  const int ha = (g_hd && hd_arg) ? hd_arg[cloud] : -1;
+  const float w_row = gcd * (2.f / (float)n), w_col = gcd * (2.f / (float)m);
+  const float inv_k = k > 0 ? 1.f / (float)k : 0.f;
+  const size_t gp = (size_t)cloud * n + p;
+  const float4 ap = P[p];
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (g_cd || ha == p) {
+    const int js = jstar[gp];
+    const float rx = ap.x - o[js], ry = ap.y - o[m + js], rz = ap.z - o[2 * m + js];
+    if (g_cd) { gx = w_row * rx; gy = w_row * ry; gz = w_row * rz; }
+    if (do_col) {
+      const int e1 = offs2[p + 1];
+      for (int e = offs2[p]; e < e1; ++e) {
+        const int j = ent2[e];
+        gx += w_col * (ap.x - o[j]); gy += w_col * (ap.y - o[m + j]); gz += w_col * (ap.z - o[2 * m + j]);
+      }
+    }
+    if (ha == p) { gx += ghd * 2.f * rx; gy += ghd * 2.f * ry; gz += ghd * 2.f * rz; }
+  }
+  if (do_curv) {
+    const float4 np_ = N[p];
+    const float f0 = ap.w * inv_k;
+    const int32_t* nbp = nbr + gp * k;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    for (int t = 0; t < k; ++t) {
+      const float4 aj = P[nbp[t]];
+      const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
+      ox += dv.x; oy += dv.y; oz += dv.z;
+    }
+    gx -= ox; gy -= oy; gz -= oz;
+    const int e1 = offs1[p + 1];
+    for (int e = offs1[p]; e < e1; ++e) {
+      const int i = ent1[e] / k;  // edge id -> source point
+      const float4 ai = P[i];
+      const float4 ni = N[i];
+      const float3 dv = dkappa_dv(ap.x - ai.x, ap.y - ai.y, ap.z - ai.z, ni.x, ni.y, ni.z, ai.w * inv_k);
+      gx += dv.x; gy += dv.y; gz += dv.z;
+    }
+  }
+  float* g = grad_adv + (size_t)cloud * 3 * n;
+  g[p] = gx; g[n + p] = gy; g[2 * n + p] = gz;
+}
+
+static bool bwd_fused_ok(int n, int m, int k, bool do_curv, bool do_col, BwdLayout* L) {
+  if (getenv("GEOA3_BWD_LARGE")) return false;  // test knob: route every call through the large-cloud path
+  if (n > 65535 || m > 65535 || (size_t)n * (size_t)(k > 0 ? k : 1) > 65535) return false;  // uint16 CSR entries
+  return plan_bwd_layout(n, m, k, do_curv, do_col, L);
+}
+
 }  // namespace geoa3
 
 
@@ -307,11 +426,19 @@ extern "C" int geoa3_kappa_loss_fwd(const float* pc, const float* normal, const 
   return GEOA3_LAUNCH_RESULT();
 }
 
+extern "C" size_t geoa3_loss_bwd_workspace_bytes(int b, int n, int m, int k) {
+  using namespace geoa3;
+  if (b <= 0 || n <= 0 || m <= 0 || k < 0) return 0;
+  BwdLayout L;
+  if (bwd_fused_ok(n, m, k, k > 0, true, &L)) return 0;  // the single-kernel path keeps everything in shared memory
+  return (size_t)b * plan_bwd_large(n, m, k).per_cloud * 4;
+}
+
 extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* nrm_adv, const float* kappa_adv,
                               const float* kappa_ori, const int32_t* jstar, const int32_t* istar,
                               const int32_t* nbr, const int32_t* hd_arg, const float* g_cd, const float* g_hd,
                               const float* g_cu, const float* g_kappa, int b, int n, int m, int k,
-                              float* grad_adv, geoa3_stream_t stream) {
+                              float* grad_adv, void* workspace, size_t workspace_bytes, geoa3_stream_t stream) {
   using namespace geoa3;
   GEOA3_CHECK_ARG(adv && grad_adv && b > 0 && n > 0 && m > 0 && k >= 0);
   if (g_cd || g_hd) GEOA3_CHECK_ARG(ori && jstar);
@@ -321,18 +448,49 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
   if (do_curv && k > 32) return GEOA3_EUNSUPPORTED;
   if (g_cu && do_curv) GEOA3_CHECK_ARG(kappa_adv && kappa_ori && jstar);
   const bool do_col = istar && g_cd;
-  if (n > 65535 || m > 65535 || (size_t)n * (size_t)(k > 0 ? k : 1) > 65535) return GEOA3_EUNSUPPORTED;  // uint16 CSR
+  if (b > 65535) return GEOA3_EUNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
   BwdLayout L;
-  if (!plan_bwd_layout(n, m, k, do_curv, do_col, &L)) return GEOA3_EUNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024 - 256);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+  if (bwd_fused_ok(n, m, k, do_curv, do_col, &L)) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024 - 256);
+      if (e != cudaSuccess) return (int)e;
+      attr_done = true;
+    }
+    loss_bwd_kernel<<<b, BW_THREADS, L.total, s>>>(adv, ori, nrm_adv, kappa_adv, kappa_ori, jstar, istar, nbr, hd_arg,
+                                                   g_cd, g_hd, g_cu, g_kappa, n, m, k, grad_adv, L);
+    return GEOA3_LAUNCH_RESULT();
   }
-  loss_bwd_kernel<<<b, BW_THREADS, L.total, (cudaStream_t)stream>>>(adv, ori, nrm_adv, kappa_adv, kappa_ori, jstar,
-                                                                    istar, nbr, hd_arg, g_cd, g_hd, g_cu, g_kappa, n,
-                                                                    m, k, grad_adv, L);
+  // large-cloud path
+  const BwdLargeLayout G = plan_bwd_large(n, m, k);
+  if (!workspace || workspace_bytes < (size_t)b * G.per_cloud * 4 || ((uintptr_t)workspace & 15)) return GEOA3_EWORKSPACE;
+  float* ws = (float*)workspace;
+  int W = 16;
+  while (W > 1 && (size_t)W * ((n + 1) & ~1) * 4 > 160 * 1024) W >>= 1;
+  const size_t hsm = (size_t)W * ((n + 1) & ~1) * 4;
+  if (hsm > 200 * 1024) return GEOA3_EUNSUPPORTED;
+  static bool attr_l = false;
+  if (!attr_l) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_large_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_l = true;
+  }
+  int err;
+  if (do_curv) {
+    bwd_large_csr_kernel<<<b, BWL_THREADS, hsm, s>>>(nbr, n * k, n, W, ws, G.per_cloud, G.offs1, G.ent1);
+    if ((err = GEOA3_LAUNCH_RESULT())) return err;
+  }
+  if (do_col) {
+    bwd_large_csr_kernel<<<b, BWL_THREADS, hsm, s>>>(istar, m, n, W, ws, G.per_cloud, G.offs2, G.ent2);
+    if ((err = GEOA3_LAUNCH_RESULT())) return err;
+  }
+  const dim3 grid(ceil_div(n, 256), b);
+  bwd_large_pack_kernel<<<grid, 256, 0, s>>>(adv, nrm_adv, kappa_adv, kappa_ori, jstar, do_curv ? g_cu : nullptr,
+                                            do_curv ? g_kappa : nullptr, n, m, do_curv, ws, G);
+  if ((err = GEOA3_LAUNCH_RESULT())) return err;
+  bwd_large_gather_kernel<<<grid, 256, 0, s>>>(ori, jstar, nbr, hd_arg, g_cd, g_hd, n, m, k, do_curv, do_col, ws, G,
+                                              grad_adv);
   return GEOA3_LAUNCH_RESULT();
 }

@@ -198,11 +198,14 @@ def loss_bwd(adv, ori=None, nrm_adv=None, kappa_adv=None, kappa_ori=None, jstar=
     for g in (g_cd, g_hd, g_cu, g_kappa):
         if g is not None:
             require_cuda_f32(g, "upstream gradient")
+    lib = _lib.load()
+    wsb = int(lib.geoa3_loss_bwd_workspace_bytes(b, n, m, k))  # 0 unless the lists outgrow shared memory
+    ws = torch.empty(wsb, device=adv.device, dtype=torch.uint8) if wsb else None
     with _guard(adv):
-        _count(1)
-        check(_lib.load().geoa3_loss_bwd(ptr(adv), ptr(ori), ptr(nrm_adv), ptr(kappa_adv), ptr(kappa_ori), ptr(jstar),
-                                         ptr(istar), ptr(nbr), ptr(hd_arg), ptr(g_cd), ptr(g_hd), ptr(g_cu),
-                                         ptr(g_kappa), b, n, m, k, ptr(grad), stream(adv)))
+        _count(1 if not wsb else 4)
+        check(lib.geoa3_loss_bwd(ptr(adv), ptr(ori), ptr(nrm_adv), ptr(kappa_adv), ptr(kappa_ori), ptr(jstar),
+                                 ptr(istar), ptr(nbr), ptr(hd_arg), ptr(g_cd), ptr(g_hd), ptr(g_cu),
+                                 ptr(g_kappa), b, n, m, k, ptr(grad), ptr(ws), wsb, stream(adv)))
     return grad
 
 

@@ -116,12 +116,17 @@ GEOA3_API int geoa3_kappa_loss_fwd(const float *pc, const float *normal, const i
  * istar / nbr (ascending source order) — deterministic, no float atomics.
  * Any of g_cd/g_hd/g_cu [b] and g_kappa [b][n] may be NULL (term skipped); istar NULL = one-sided CD.
  * grad_adv [b][3][n] is fully overwritten.
+ * Clouds whose lists do not fit shared memory (n*k > 65535 edges, e.g. n >= 4096 at k = 16) take the same
+ * gather with the lists in a caller-provided device workspace of geoa3_loss_bwd_workspace_bytes(b,n,m,k)
+ * bytes (16-byte aligned; 0 = not needed, workspace may be NULL): identical summation order, identical bits.
  * Replaces: autograd through pytorch3d _knn_points.backward + knn_gather scatter_add (float atomics),
  *           reached from Attacker/geoA3_attack.py:326. */
+GEOA3_API size_t geoa3_loss_bwd_workspace_bytes(int b, int n, int m, int k);
 GEOA3_API int geoa3_loss_bwd(const float *adv, const float *ori, const float *nrm_adv, const float *kappa_adv,
                    const float *kappa_ori, const int32_t *jstar, const int32_t *istar, const int32_t *nbr,
                    const int32_t *hd_arg, const float *g_cd, const float *g_hd, const float *g_cu,
-                   const float *g_kappa, int b, int n, int m, int k, float *grad_adv, geoa3_stream_t stream);
+                   const float *g_kappa, int b, int n, int m, int k, float *grad_adv, void *workspace,
+                   size_t workspace_bytes, geoa3_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
  * pointnet2_ops  (replaces the 9 functions exported by _ext-src/src/bindings.cpp:6-19)

@@ -132,3 +132,18 @@ def test_attack_trajectory_matches_cpu_port():
         assert np.abs(got[-1] - got[0]).max() > 1e-3                         # the optimisation actually moved
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize("n,k", [(4096, 16), (10000, 32)])
+def test_attack_runs_at_sweep_sizes(n, k):
+    """BASELINE config[3] cloud sizes through the whole attack step (pruned searches, large-cloud backward, CUDA
+    graph): graph replay == eager, finite losses."""
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=3, curv_loss_knn=k)
+    data = _data(2, n)
+    out_g = atk.attack(net, data, cfg, use_cuda_graph=True)
+    out_e = atk.attack(net, data, cfg, use_cuda_graph=False)
+    lg, le = np.asarray(out_g[4]), np.asarray(out_e[4])
+    assert np.isfinite(lg).all() and np.allclose(lg, le, rtol=1e-4, atol=1e-5)

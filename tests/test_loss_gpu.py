@@ -457,3 +457,41 @@ def test_defense_filters_vs_reference_golden():
         assert num == int(drop) and out.shape == (1, 3, pc.shape[2] - int(drop))
         i += 1
     assert i == 3
+
+
+def test_backward_large_clouds():
+    """Clouds whose neighbour lists outgrow shared memory (n*k > 65535 edges: BASELINE config[3] sizes) take the
+    global-workspace backward: gradients vs the oracle, and bit-identical to the fused kernel where both apply."""
+    import os
+
+    from geoa3_b200 import loss_utils as L
+    from geoa3_b200 import ops
+
+    for (b, n, k, std) in ((2, 4096, 16, 1e-2), (1, 2500, 32, 3e-2)):
+        adv, ori, nrm = make(b, n, 1, std)
+        assert ops._lib.load().geoa3_loss_bwd_workspace_bytes(b, n, n, k) > 0
+        a = cu(adv).requires_grad_(True)
+        ko = L._get_kappa_ori(cu(ori), cu(nrm), k)
+        tot, cd, hd, cur = L.geo_loss(a, cu(ori), cu(nrm), ko, k, 1.0, 0.1, 1.0)
+        tot.sum().backward()
+        ko_o, _ = O.kappa_ori(ori, nrm, k)
+        fwd = O.geo_forward(adv, ori, nrm, ko_o, k)
+        g = np.ones(b)
+        want = O.geo_backward(adv, ori, fwd, ko_o, g * 1.0, g * 0.1, g * 1.0)
+        assert rel_err(a.grad.cpu().numpy(), want) < TOL
+        L.clear_cache()
+    # same inputs through both paths
+    adv, ori, nrm = make(3, 700, 4, 2e-2)
+    grads = []
+    for force in (False, True):
+        if force:
+            os.environ["GEOA3_BWD_LARGE"] = "1"
+        try:
+            a = cu(adv).requires_grad_(True)
+            ko = L._get_kappa_ori(cu(ori), cu(nrm), 16)
+            L.geo_loss(a, cu(ori), cu(nrm), ko, 16, 1.0, 0.1, 1.0)[0].sum().backward()
+            grads.append(a.grad.clone())
+        finally:
+            os.environ.pop("GEOA3_BWD_LARGE", None)
+        L.clear_cache()
+    assert torch.equal(grads[0], grads[1])
