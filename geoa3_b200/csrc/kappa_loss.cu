@@ -90,13 +90,29 @@ kappa_loss_fwd_kernel(const float* __restrict__ pc, const float* __restrict__ no
       const float4 pi = pts[i];
       const int32_t* nbi = nbr + gi * k;
       float acc = 0.f;
-      for (int t = 0; t < k; ++t) {
-        const float4 pj = pts[nbi[t]];
+      auto term = [&](int j) {
+        const float4 pj = pts[j];
         const float vx = pj.x - pi.x, vy = pj.y - pi.y, vz = pj.z - pi.z;
         // v / max(|v|, 1e-12): |v| >= 1e-12 <=> |v|^2 >= 1e-24; MUFU.RSQ is accurate to ~1e-7 relative
         const float s2 = vx * vx + vy * vy + vz * vz;
         const float inv = s2 >= 1e-24f ? rsqrtf(s2) : 1e12f;
         acc += fabsf((vx * nx + vy * ny + vz * nz) * inv);
+      };
+      if ((k & 3) == 0) {
+        // 16-byte index rows: up to 16 neighbour indices are in flight before the first one is used (a scalar
+        // load per neighbour put k dependent global round trips on every thread's critical path)
+        const int4* nb4 = reinterpret_cast<const int4*>(nbi);
+        const int k4 = k >> 2;
+        for (int t = 0; t < k4; t += 4) {
+          int4 q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) q[u] = t + u < k4 ? nb4[t + u] : make_int4(0, 0, 0, 0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (t + u < k4) { term(q[u].x); term(q[u].y); term(q[u].z); term(q[u].w); }
+        }
+      } else {
+        for (int t = 0; t < k; ++t) term(nbi[t]);
       }
       kap = acc * inv_k;
       if (kappa) kappa[gi] = kap;
