@@ -565,23 +565,28 @@ csr_gather_grad_coop_kernel(const float* __restrict__ grad_out, const int* __res
 // fwd_order_ok_kernel verifies the shape on the device (violations counter); if any row deviates this kernel
 // returns immediately and the generic CSR path (launched right after, predicated the other way) does the work.
 __global__ void fwd_order_ok_kernel(const int32_t* __restrict__ idx, int rows, int ns, int n, int* __restrict__ violations) {
+  // one pass, one load per entry: a row is fine iff r[0] is in range, the entries before the first repeat of r[0]
+  // are strictly ascending (and < n), and everything from that repeat on equals r[0]
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int32_t* r = idx + (size_t)row * ns;
   const int p0 = r[0];
   bool bad = p0 < 0 || p0 >= n;
-  // first position >= 1 holding p0 again = start of the padding suffix
-  int cnt = ns;
-  for (int k0 = 0; k0 < ns && cnt == ns; k0 += 32) {
+  bool in_pad = false;   // warp-uniform: the padding suffix has started in an earlier chunk
+  int carry = p0;        // last entry of the previous chunk
+  for (int k0 = 0; k0 < ns; k0 += 32) {
     const int k = k0 + lane;
-    const unsigned hit = __ballot_sync(0xffffffffu, k >= 1 && k < ns && r[k] == p0);
-    if (hit) cnt = k0 + __ffs(hit) - 1;
-  }
-  for (int k = 1 + lane; k < ns; k += 32) {
-    const int v = r[k];
-    if (k < cnt) bad |= !(v > r[k - 1]) || v >= n;
-    else bad |= v != p0;
+    const bool live = k < ns;
+    const int v = live ? r[k] : p0;
+    int prev = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) prev = carry;
+    const unsigned pad = __ballot_sync(0xffffffffu, live && k >= 1 && v == p0);
+    // first padding position of this chunk (or 32); entries at or after it must all be p0
+    const int fp = in_pad ? 0 : (pad ? __ffs(pad) - 1 : 32);
+    if (live && k >= 1) bad |= lane >= fp ? v != p0 : (!(v > prev) || v >= n);
+    in_pad = in_pad || pad != 0u;
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(violations, 1);
 }

@@ -233,3 +233,31 @@ def test_query_and_group_module():
     gx = O.group_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx) - new_xyz.cpu().numpy().transpose(0, 2, 1)[..., None]
     assert np.allclose(out[:, :3].cpu().numpy(), gx, atol=0, rtol=0)
     assert pu.GroupAll()(X, None, feats).shape == (2, 8, 1, 256)
+
+
+def test_group_grad_row_shape_check_edges():
+    """Rows at the edge of the ball-query shape: padding that starts exactly on a 32-entry boundary (valid), a stray
+    index after the padding began, an equal neighbour pair, an index >= n in the ascending part (all invalid => the
+    generic path must take over).  Whatever path runs, the gradient must equal the oracle's."""
+    from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
+
+    rng = np.random.default_rng(5)
+    b, c, n, m, ns = 2, 12, 400, 24, 64
+    base = np.sort(rng.choice(n - 1, (b, m, ns), replace=True), axis=2).astype(np.int32)
+    for i in range(b):
+        for j in range(m):  # strictly ascending rows
+            base[i, j] = np.sort(rng.choice(n - 1, ns, replace=False))
+    feats = rng.standard_normal((b, c, n)).astype(np.float32)
+    go = rng.standard_normal((b, c, m, ns)).astype(np.float32)
+
+    def check(idx):
+        f = cu(feats).requires_grad_(True)
+        pu.grouping_operation(f, cu(idx)).backward(cu(go))
+        assert rel_err(f.grad.cpu().numpy(), O.group_points_grad(go, idx, n)) < 1e-5
+
+    v = base.copy(); v[:, :, 32:] = v[:, :, :1]; check(v)                      # valid: padding from position 32
+    v = base.copy(); v[:, ::2, 17:] = v[:, ::2, :1]; check(v)                  # valid: padding from position 17
+    w = v.copy(); w[0, 0, 40] = w[0, 0, 5]; check(w)                           # stray index inside the padding
+    w = base.copy(); w[1, 3, 50] = w[1, 3, 49]; check(w)                       # equal neighbours, not the first index
+    w = base.copy(); w[1, 3, 33] = w[1, 3, 31]; check(w)                       # descending across the chunk boundary
+    w = v.copy(); w[0, 2, 63] = (w[0, 2, 0] + 1) % n; check(w)                 # last entry leaves the padding
