@@ -55,7 +55,7 @@ def test_result_files_roundtrip(tmp_path):
     name = provider.result_name(12, 3, 17, 17)
     provider.save_adversarial(str(tmp_path), name, pc, 3, 17, est_normal=nr)
     rec = loadmat(str(tmp_path / "Mat" / (name + ".mat")))
-    assert np.array_equal(rec["adversary_point_clouds"], pc) and int(rec["gt_label"]) == 3 and int(rec["attack_label"]) == 17
+    assert np.array_equal(rec["adversary_point_clouds"], pc) and int(rec["gt_label"].item()) == 3 and int(rec["attack_label"].item()) == 17
     assert np.array_equal(rec["est_normal"], nr)
     rows = open(str(tmp_path / "PC" / (name + ".obj"))).read().splitlines()
     assert len(rows) == 128 and rows[0].startswith("v ") and rows[0].endswith(" 0 0 0")
