@@ -26,6 +26,7 @@ SIGNATURES = {
     "geoa3_loss_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "geoa3_loss_bwd": (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "geoa3_furthest_point_sampling": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "geoa3_farthest_points_sample": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "geoa3_gather_points": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "geoa3_gather_points_grad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "geoa3_ball_query": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp]),

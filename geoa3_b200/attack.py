@@ -30,7 +30,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import loss_utils, ops
+from . import loss_utils, ops, utility
 from .utility import _compare
 
 # flag defaults of the reference CLI (main_attack.py:317-384)
@@ -164,6 +164,7 @@ class AttackState(object):
         self.gamma = 0.9990
         self.graph = None
         self.hints = loss_utils.HintBuffers()  # previous step's argmin / kNN indices seed the next search
+        self.subsample = bool(_get(cfg, "is_subsample_opt")) and n > _get(cfg, "npoint")
 
     def reset_global(self):
         """Back to the state of a fresh attack() call (used after the CUDA-graph warm-up/capture)."""
@@ -198,12 +199,25 @@ class AttackState(object):
         """One inner iteration (:238-368): forward, bookkeeping, losses, backward, optimiser step."""
         cfg = self.cfg
         input_all = self.pc_ori + self.offset
+        # --is_subsample_opt (:283-296): a cloud denser than the victim's input size is farthest-point subsampled
+        # (fresh random first pick) for the forward of every step; the losses then compare that subsample with the
+        # full original cloud, and success is a majority vote over `eval_num` independent subsamples
+        sub = self.subsample
+        input_curr = utility.farthest_points_sample(input_all, _get(cfg, "npoint")) if sub else input_all
         logits, loss, loss_n, cls_loss, dis, hd, cu, constrain = forward_step(
-            self.net, self.pc_ori, input_all, self.normal_ori, self.kappa_ori, self.target, self.scale_const, cfg,
-            self.targeted, loss_divisor=self.global_batch, hints=self.hints)
+            self.net, self.pc_ori, input_curr, self.normal_ori, self.kappa_ori, self.target, self.scale_const, cfg,
+            self.targeted, loss_divisor=self.global_batch, hints=loss_utils.NO_HINTS if sub else self.hints)
         with torch.no_grad():
-            pred = logits.argmax(1)
-            success = _compare(pred, self.target, self.gt_target, self.targeted)
+            if sub:
+                ev = max(1, int(_get(cfg, "eval_num")))
+                votes = self.net(utility.farthest_points_sample(input_all.detach().repeat_interleave(ev, 0),
+                                                                _get(cfg, "npoint"))).argmax(1).view(self.b, ev)
+                hit = _compare(votes, self.target[:, None], self.gt_target[:, None], self.targeted)
+                success = hit.sum(1).to(torch.float32) > 0.5 * ev
+                pred = votes.mode(1).values
+            else:
+                pred = logits.argmax(1)
+                success = _compare(pred, self.target, self.gt_target, self.targeted)
             metric = self.prev_constrain  # value of the previous step, as in the reference (:301 before :319)
             better = success & (metric < self.best_loss)
             self.best_loss.copy_(torch.where(better, metric, self.best_loss))
@@ -305,7 +319,7 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
 
     Extra keyword arguments (all optional): `global_batch` / `rows` describe the shard of a larger batch
     this process owns (loss scaling + initial offsets), `use_cuda_graph` replays the captured step."""
-    for flag in ("is_partial_var", "is_subsample_opt", "is_pre_jitter_input"):
+    for flag in ("is_partial_var", "is_pre_jitter_input"):
         if _get(cfg, flag):
             raise NotImplementedError("--%s is outside the B200 hot path (see DESIGN.md, out of scope)" % flag)
     device = device or torch.device("cuda", torch.cuda.current_device())
@@ -315,7 +329,7 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
     gb = global_batch if global_batch is not None else b
     st = AttackState(net, pc_ori, normal_ori, target, gt_target, cfg, targeted, global_batch=gb)
     steps = _get(cfg, "iter_max_steps")
-    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler")
+    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample  # (random first picks)
     if graphable:
         st.begin_search_step(0, default_offsets(gb, n, 0, seed, rows).to(device))
         st.capture()

@@ -34,7 +34,8 @@ static int ref_fps_block(int n) {
 
 template <int P>
 __global__ void __launch_bounds__(1024)
-fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs) {
+fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs,
+           const int32_t* __restrict__ start) {
   extern __shared__ __align__(16) float s_xyz[];  // [3][n] SoA mirror of the cloud
   __shared__ unsigned long long s_part[2][FPS_MAX_WARPS];
 
@@ -43,13 +44,15 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits
   const float* p = xyz + (size_t)cloud * n * 3;
   int32_t* out = idxs + (size_t)cloud * m;
 
+  // start != nullptr: plain FPS of Lib/utility.py:175-187 (given first pick, no frozen points, ties -> lowest index)
+  const bool plain = start != nullptr;
   float px[P], py[P], pz[P], temp[P];
   unsigned tk[P];  // low word of the sort key; 0 => point is frozen (skipped) or out of range
 #pragma unroll
   for (int t = 0; t < P; ++t) {
     const int k = tid + t * T;
     px[t] = py[t] = pz[t] = 0.f;
-    temp[t] = 1e10f;
+    temp[t] = plain ? 3.0e38f : 1e10f;
     tk[t] = 0u;
     if (k < n) {
       px[t] = p[k * 3]; py[t] = p[k * 3 + 1]; pz[t] = p[k * 3 + 2];
@@ -59,13 +62,13 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits
       // among equal distances the winner has the smallest bit-reversed thread id; inside one reference
       // thread (k = tid, tid+BS, ...) the strict '>' keeps the smallest k.
       const unsigned rtid = ref_bits ? (__brev((unsigned)(k % ref_bs)) >> (32 - ref_bits)) : 0u;
-      if (!((double)mag <= 1e-3)) tk[t] = ~((rtid << 20) | (unsigned)k);
+      if (plain || !((double)mag <= 1e-3)) tk[t] = ~((rtid << 20) | (unsigned)k);
     }
   }
-  if (tid == 0) out[0] = 0;
+  int old = plain ? min(max(start[cloud], 0), n - 1) : 0;
+  if (tid == 0) out[0] = old;
   __syncthreads();
 
-  int old = 0;
   for (int j = 1; j < m; ++j) {
     const float x1 = s_xyz[old], y1 = s_xyz[n + old], z1 = s_xyz[2 * n + old];
     // branch-free update: frozen / out-of-range points carry tk == 0 and contribute the minimal key (0,0)
@@ -186,7 +189,8 @@ constexpr int FPSQ_WARPS = 4;
 
 template <int P>
 __global__ void __launch_bounds__(FPSQ_WARPS * 32)
-fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs) {
+fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs,
+                const int32_t* __restrict__ start) {
   static_assert(P % 2 == 0, "points are packed in pairs");
   extern __shared__ __align__(16) float s_xyz[];  // [3][n] SoA mirror (broadcast of the last pick), then int s_out[m]
   __shared__ __align__(16) unsigned long long s_part[2][FPSQ_WARPS];
@@ -197,6 +201,7 @@ fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref
   const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float* p = xyz + (size_t)cloud * n * 3;
   int32_t* out = idxs + (size_t)cloud * m;
+  const bool plain = start != nullptr;  // Lib/utility.py:175-187 semantics (see fps_kernel)
   float2 px[H], py[H], pz[H], temp[H];
   unsigned tk[P];
 #pragma unroll
@@ -209,14 +214,17 @@ fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref
       s_xyz[k] = x; s_xyz[n + k] = y; s_xyz[2 * n + k] = z;
       const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
       const unsigned rtid = ref_bits ? (__brev((unsigned)(k % ref_bs)) >> (32 - ref_bits)) : 0u;
-      if (!((double)mag <= 1e-3)) { tk[t] = ~((rtid << 20) | (unsigned)k); t0 = 1e10f; }  // else frozen: temp 0, key 0
+      if (plain || !((double)mag <= 1e-3)) {  // else frozen: temp 0, key 0
+        tk[t] = ~((rtid << 20) | (unsigned)k);
+        t0 = plain ? 3.0e38f : 1e10f;
+      }
     }
     if (t & 1) { px[t >> 1].y = x; py[t >> 1].y = y; pz[t >> 1].y = z; temp[t >> 1].y = t0; }
     else { px[t >> 1].x = x; py[t >> 1].x = y; pz[t >> 1].x = z; temp[t >> 1].x = t0; }
   }
-  if (tid == 0) s_out[0] = 0;
+  int old = plain ? min(max(start[cloud], 0), n - 1) : 0;
+  if (tid == 0) s_out[0] = old;
   __syncthreads();
-  int old = 0;
   for (int j = 1; j < m; ++j) {
     const float x1 = -s_xyz[old], y1 = -s_xyz[n + old], z1 = -s_xyz[2 * n + old];
     const float2 nx = make_float2(x1, x1), ny = make_float2(y1, y1), nz = make_float2(z1, z1);
@@ -998,8 +1006,9 @@ static int run_group_grad(const float* grad_out, const int32_t* idx, int b, int 
 
 using namespace geoa3;
 
-extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int m, int32_t* idx,
-                                             geoa3_stream_t stream) {
+// start == nullptr: pointnet2 semantics (first pick 0, frozen points, reference tie order);
+// start != nullptr: plain FPS from the given first picks (Lib/utility.py:175-187)
+static int run_fps(const float* xyz, int b, int n, int m, const int32_t* start, int32_t* idx, geoa3_stream_t stream) {
   GEOA3_CHECK_ARG(xyz && idx && b > 0 && n > 0 && m > 0);
   if (n >= (1 << 20) || (size_t)n * 12 > 200 * 1024) return GEOA3_EUNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1007,6 +1016,7 @@ extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int
   const int bs = ref_fps_block(n);
   int bits = 0;
   while ((1 << bits) < bs) ++bits;
+  if (start) bits = 0;  // ties -> lowest index
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(fps_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1015,30 +1025,41 @@ extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  const bool one_warp = getenv("GEOA3_FPS_WARP") != nullptr;  // A/B knob for tools/time_kernels.py, not part of the API
+  const bool one_warp = !start && getenv("GEOA3_FPS_WARP") != nullptr;  // A/B knob for tools/time_kernels.py, not part of the API
   if (one_warp && n <= 512) {
     fps_warp_kernel<16><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
   } else if (one_warp && n <= 1024) {
     fps_warp_kernel<32><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
   } else if (n <= 256) {
-    fps_quad_kernel<2><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+    fps_quad_kernel<2><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
   } else if (n <= 512) {
-    fps_quad_kernel<4><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+    fps_quad_kernel<4><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
   } else if (n <= 1024) {
-    fps_quad_kernel<8><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+    fps_quad_kernel<8><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
   } else if (n <= 2048) {
-    fps_quad_kernel<16><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx);
+    fps_quad_kernel<16><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
   } else if (n <= 4096) {
     const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
-    fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx);
+    fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx, start);
   } else if (n <= 8192) {
-    fps_kernel<8><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx);
+    fps_kernel<8><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx, start);
   } else if (n <= 16384) {
-    fps_kernel<16><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx);
+    fps_kernel<16><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx, start);
   } else {
     return GEOA3_EUNSUPPORTED;
   }
   return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int m, int32_t* idx,
+                                             geoa3_stream_t stream) {
+  return run_fps(xyz, b, n, m, nullptr, idx, stream);
+}
+
+extern "C" int geoa3_farthest_points_sample(const float* xyz, int b, int n, int m, const int32_t* start, int32_t* idx,
+                                            geoa3_stream_t stream) {
+  GEOA3_CHECK_ARG(start);
+  return run_fps(xyz, b, n, m, start, idx, stream);
 }
 
 extern "C" int geoa3_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius,

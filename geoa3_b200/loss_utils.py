@@ -46,7 +46,7 @@ from . import ops
 
 __all__ = ["norm_l2_loss", "chamfer_loss", "pseudo_chamfer_loss", "hausdorff_loss", "_get_kappa_ori",
            "_get_kappa_adv", "curvature_loss", "displacement_loss", "corresponding_normal_loss", "repulsion_loss",
-           "distance_kmean_loss", "kNN_smoothing_loss", "uniform_loss", "geo_loss", "clear_cache", "HintBuffers"]
+           "distance_kmean_loss", "kNN_smoothing_loss", "uniform_loss", "geo_loss", "clear_cache", "HintBuffers", "NO_HINTS"]
 
 
 # ---------------------------------------------------------------------------- search hints
@@ -76,6 +76,8 @@ class HintBuffers(object):
             self.istar = torch.arange(m, device=dev, dtype=torch.int32).clamp_(max=n - 1).repeat(b, 1)
 
 
+NO_HINTS = object()  # pass as `hints` when consecutive calls see unrelated clouds (e.g. a fresh random subsample each
+                     # step): stale indices are still exact as seeds, but they cost more than searching unseeded
 _LAST = {}  # (device, b, n, m) -> last results, reused as (non-aliased) hints by the plain reference API
 _ORDER = {}  # id(ori) -> (weakref(ori), version, perm, iperm, ori_arranged): visiting order of a cloud seen before
 
@@ -148,7 +150,9 @@ def _nn(e, both):
         b, _, n = e.adv_c.shape
         m = e.ori_c.shape[2]
         hb = e.hints
-        if hb is not None:  # persistent buffers: hint and result alias, refreshed in place
+        if hb is NO_HINTS:
+            e.d1, e.jstar, e.d2, e.istar = ops.nn_pair(e.adv_c, e.ori_c, both=True)
+        elif hb is not None:  # persistent buffers: hint and result alias, refreshed in place
             hb.ensure_nn(b, n, m, e.adv_c.device)
             if n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
                 hb.ensure_order(e.ori_c)
@@ -187,7 +191,9 @@ def _reductions(e):
 def _nbr(e, k):
     if k not in e.nbr:
         hb = e.hints
-        if hb is not None:
+        if hb is NO_HINTS:
+            e.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1)[0]
+        elif hb is not None:
             buf = hb.nbr.get(k)
             if buf is None or buf.shape[:2] != e.adv_c.shape[::2]:
                 hb.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1)[0]  # first call: nothing to hint with

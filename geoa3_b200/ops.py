@@ -209,6 +209,18 @@ def loss_bwd(adv, ori=None, nrm_adv=None, kappa_adv=None, kappa_ori=None, jstar=
     return grad
 
 
+def farthest_points_sample_idx(points, nsamples, start):
+    """points [b,n,3] f32, start [b] int32 -> idx [b,nsamples] int32: plain FPS from the given first picks
+    (geoa3_farthest_points_sample; Lib/utility.py:175-187 semantics)."""
+    require_cuda_f32(points, "points"); require_cuda_i32(start, "start")
+    b, n, _ = points.shape
+    out = torch.empty(b, nsamples, device=points.device, dtype=torch.int32)
+    with _guard(points):
+        _count(1)
+        check(_lib.load().geoa3_farthest_points_sample(ptr(points), b, n, nsamples, ptr(start), ptr(out), stream(points)))
+    return out
+
+
 # ------------------------------------------------------------------ pointnet2_ops (bindings.cpp:6-19 names)
 def furthest_point_sampling(points, nsamples):
     require_cuda_f32(points, "points")

@@ -136,6 +136,15 @@ GEOA3_API int geoa3_loss_bwd(const float *adv, const float *ori, const float *nr
  * furthest_point_sampling (sampling.cpp:66-87, sampling_gpu.cu:69-229).  No temp buffer needed. */
 GEOA3_API int geoa3_furthest_point_sampling(const float *xyz, int b, int n, int m, int32_t *idx, geoa3_stream_t stream);
 
+/* Plain farthest point sampling from a given first pick per cloud: start[b] (int32, clamped to [0,n)), no frozen
+ * points, running minimum from +inf, arg-max ties -> lowest index; idx[b][m] int32 with idx[.][0] = start.
+ * Replaces: farthest_points_sample, Lib/utility.py:175-187 (a Python loop of m-1 torch.min / argmax passes), the
+ * per-iteration subsampling of --is_subsample_opt (Attacker/geoA3_attack.py:283-292).  Squared distances (same
+ * fp32 chain as the other sampling kernels) instead of the reference's norm: same pick except where sqrt
+ * rounding merges two different squared distances. */
+GEOA3_API int geoa3_farthest_points_sample(const float *xyz, int b, int n, int m, const int32_t *start, int32_t *idx,
+                                           geoa3_stream_t stream);
+
 /* points [b][c][n], idx [b][m] -> out [b][c][m]        (gather_points, sampling.cpp:15-39) */
 GEOA3_API int geoa3_gather_points(const float *points, const int32_t *idx, int b, int c, int n, int m, float *out,
                         geoa3_stream_t stream);

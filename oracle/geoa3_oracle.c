@@ -283,6 +283,36 @@ ORC_API void orc_fps(const float *xyz, int b, int n, int m, int32_t *idxs) {
   free(temp); free(dists); free(dists_i);
 }
 
+/* Lib/utility.py:175-187 farthest_points_sample: plain FPS from a given start index per cloud — no frozen points,
+ * arg-max ties -> lowest index (torch.argmax), running minimum initialised to +inf.  The reference measures the
+ * Euclidean norm; the squared distance used here (same fp32 chain as the kernels) selects the same point except
+ * where sqrt rounding merges two different squared distances.  xyz AoS [b][n][3]. */
+ORC_API void orc_fps_from(const float *xyz, int b, int n, int m, const int32_t *start, int32_t *idxs) {
+  if (m <= 0) return;
+  float *temp = (float *)malloc(sizeof(float) * n);
+  for (int c = 0; c < b; ++c) {
+    const float *p = xyz + (size_t)c * n * 3;
+    int32_t *out = idxs + (size_t)c * m;
+    for (int k = 0; k < n; ++k) temp[k] = INFINITY;
+    int old = start[c];
+    out[0] = old;
+    for (int j = 1; j < m; ++j) {
+      float x1 = p[old * 3], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
+      float best = -1.f;
+      int besti = 0;
+      for (int k = 0; k < n; ++k) {
+        float d = dist2f_pn2(p[k * 3], p[k * 3 + 1], p[k * 3 + 2], x1, y1, z1);
+        float d2 = fminf(d, temp[k]);
+        temp[k] = d2;
+        if (d2 > best) { best = d2; besti = k; }
+      }
+      old = besti;
+      out[j] = old;
+    }
+  }
+  free(temp);
+}
+
 /* ball_query_gpu.cu:9-44 (+ ball_query.cpp:19-21 zero init). AoS inputs. */
 ORC_API void orc_ball_query(const float *new_xyz, const float *xyz, int b, int n, int m, float radius,
                             int nsample, int32_t *idx) {

@@ -226,6 +226,15 @@ def fps(xyz, m):
     return out
 
 
+def fps_from(xyz, m, start):
+    """xyz [b,n,3], start [b] -> idx [b,m] i32: plain FPS from given start indices (Lib/utility.py:175-187)."""
+    xyz, start = _f32(xyz), _i32(start)
+    b, n, _ = xyz.shape
+    out = np.zeros((b, m), np.int32)
+    lib().orc_fps_from(_vp(xyz), b, n, m, _vp(start), _vp(out))
+    return out
+
+
 def ball_query(new_xyz, xyz, radius, nsample):
     new_xyz, xyz = _f32(new_xyz), _f32(xyz)
     b, n, _ = xyz.shape

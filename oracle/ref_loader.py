@@ -212,3 +212,22 @@ def defense_outputs(pc, drop_num, alpha, outlier_knn):
     var_pc, var_num = d.outlier_removal_fn(t, "outliers_variance", drop_num, alpha, outlier_knn)
     fix_pc, fix_num = d.outlier_removal_fn(t, "outliers_fixNum", drop_num, alpha, outlier_knn)
     return dict(var_pc=var_pc.numpy(), var_num=np.int64(var_num), fix_pc=fix_pc.numpy(), fix_num=np.int64(fix_num))
+
+
+def ref_farthest_points_sample(points, num_points, start):
+    """Executes the reference's farthest_points_sample (Lib/utility.py:175-187) IN PLACE: the function's own AST
+    node is compiled from /root/reference (the module itself cannot be imported: seaborn / matplotlib / tty), with
+    its random first pick replaced by `start` and `.cuda()` neutralised.  points [b,3,n] -> [b,3,num_points]."""
+    import ast
+
+    src = open(osp.join(REF_ROOT, "Lib", "utility.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "farthest_points_sample"][0]
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module([fn], []), osp.join(REF_ROOT, "Lib", "utility.py"), "exec"), ns)
+    saved = (torch.randint, torch.Tensor.cuda)
+    torch.randint = lambda *a, **k: torch.from_numpy(np.asarray(start, np.int64))[:, None]
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return ns["farthest_points_sample"](torch.from_numpy(np.asarray(points, np.float32)), num_points).numpy()
+    finally:
+        torch.randint, torch.Tensor.cuda = saved

@@ -23,6 +23,7 @@ CASES = [
     ("loss_b2_n500_k8", 2, 500, 8, 1e-3, 3),     # ragged n, reference-sized initial perturbation
     ("loss_b4_n128_k16_big", 4, 128, 16, 1e-1, 6),  # large perturbation: many-to-one argmins, empty columns
 ]
+FPS_CASES = [(3, 2048, 256), (2, 1000, 100), (1, 5000, 64), (2, 300, 300)]   # b, n, picks
 DEFENSE_CASES = [  # n, outlier_knn, alpha, drop_num, offset std
     (1024, 2, 1.1, 50, 1e-2),
     (700, 8, 0.5, 123, 3e-2),
@@ -34,7 +35,7 @@ AUX_CASES = [
 ]
 
 
-def main(which=("loss", "aux", "defense")):
+def main(which=("loss", "aux", "defense", "fps")):
     torch.manual_seed(0)
     torch.set_num_threads(4)
     for name, b, n, k, std, start in (CASES if "loss" in which else []):
@@ -76,6 +77,17 @@ def main(which=("loss", "aux", "defense")):
             print("defense case", i, "removed", out["c%d_var_num" % i], out["c%d_fix_num" % i])
         np.savez_compressed(osp.join(HERE, "defense_cases.npz"), **out)
 
+    # farthest_points_sample (Lib/utility.py:175-187) with fixed first picks
+    if "fps" in which:
+        out = {}
+        for i, (b, n, m) in enumerate(FPS_CASES):
+            pc, _, _ = synth.make_batch(b, n, 3 * i)
+            start = np.random.default_rng(i).integers(0, n, b).astype(np.int32)
+            out["c%d_pc" % i], out["c%d_start" % i] = pc, start
+            out["c%d_sel" % i] = ref_loader.ref_farthest_points_sample(pc, m, start)
+            print("fps case", i, out["c%d_sel" % i].shape)
+        np.savez_compressed(osp.join(HERE, "fps_plain_cases.npz"), **out)
+
 
 if __name__ == "__main__":
-    main(tuple(sys.argv[1:]) or ("loss", "aux", "defense"))   # e.g. `make_golden.py aux` regenerates only aux_*
+    main(tuple(sys.argv[1:]) or ("loss", "aux", "defense", "fps"))   # e.g. `make_golden.py aux` regenerates only aux_*

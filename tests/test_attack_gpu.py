@@ -147,3 +147,18 @@ def test_attack_runs_at_sweep_sizes(n, k):
     out_e = atk.attack(net, data, cfg, use_cuda_graph=False)
     lg, le = np.asarray(out_g[4]), np.asarray(out_e[4])
     assert np.isfinite(lg).all() and np.allclose(lg, le, rtol=1e-4, atol=1e-5)
+
+
+def test_attack_subsample_opt():
+    """--is_subsample_opt (geoA3_attack.py:283-296): a 2048-point cloud attacked through a 512-point victim input;
+    every step draws fresh farthest-point subsamples; the full cloud is what gets optimised and returned."""
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=8, curv_loss_knn=8, npoint=512, is_subsample_opt=True, eval_num=3)
+    data = _data(2, 2048)
+    torch.manual_seed(1)
+    best, target, success, steps, losses = atk.attack(net, data, cfg)
+    L = np.asarray(losses)
+    assert best.shape == (2, 3, 2048) and L.shape == (8, 2) and np.isfinite(L).all()
+    assert not np.allclose(L[0], L[-1])

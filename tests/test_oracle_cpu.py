@@ -149,3 +149,21 @@ def test_oracle_regularisers_match_reference_golden(path):
         assert rel_err(v, g["f64_" + key]) < 1e-12, key
         assert rel_err(v, g["f32_" + key]) < 1e-5, key
     assert abs(O.uniform_loss(g["adv"]) - float(g["f64_uniform"])) < 1e-10 * float(g["f64_uniform"])
+
+
+def test_oracle_plain_fps_matches_reference_golden():
+    """farthest_points_sample (Lib/utility.py:175-187): the C restatement picks the same points as the reference
+    function executed in place (fixture tests/golden/fps_plain_cases.npz; fixed first picks)."""
+    import os.path as osp
+
+    from helpers import GOLDEN_DIR
+
+    g = np.load(osp.join(GOLDEN_DIR, "fps_plain_cases.npz"))
+    i = 0
+    while "c%d_pc" % i in g:
+        pc, start, sel = g["c%d_pc" % i], g["c%d_start" % i], g["c%d_sel" % i]
+        idx = O.fps_from(np.ascontiguousarray(pc.transpose(0, 2, 1)), sel.shape[2], start)
+        assert np.array_equal(idx[:, 0], start)
+        assert np.array_equal(np.stack([pc[c][:, idx[c]] for c in range(pc.shape[0])]), sel)
+        i += 1
+    assert i == 4

@@ -261,3 +261,33 @@ def test_group_grad_row_shape_check_edges():
     w = base.copy(); w[1, 3, 50] = w[1, 3, 49]; check(w)                       # equal neighbours, not the first index
     w = base.copy(); w[1, 3, 33] = w[1, 3, 31]; check(w)                       # descending across the chunk boundary
     w = v.copy(); w[0, 2, 63] = (w[0, 2, 0] + 1) % n; check(w)                 # last entry leaves the padding
+
+
+def test_plain_fps_vs_oracle_and_reference_golden():
+    """geoa3_farthest_points_sample (Lib/utility.py:175-187 semantics): indices bit-exact vs the C oracle for every
+    kernel variant (n = 37 ... 5000), the reference function's own picks (golden), and gradient through the gather."""
+    import os.path as osp
+
+    from geoa3_b200 import ops, utility
+    from helpers import GOLDEN_DIR
+
+    rng = np.random.default_rng(9)
+    for (b, n, m) in ((3, 37, 20), (4, 256, 256), (3, 500, 77), (5, 1024, 512), (2, 2048, 100), (2, 4096, 300),
+                      (1, 10000, 128)):
+        xyz = clouds(b, n, 1)
+        start = rng.integers(0, n, b).astype(np.int32)
+        got = ops.farthest_points_sample_idx(cu(xyz), m, cu(start)).cpu().numpy()
+        assert np.array_equal(got, O.fps_from(xyz, m, start)), (b, n, m)
+    g = np.load(osp.join(GOLDEN_DIR, "fps_plain_cases.npz"))
+    i = 0
+    while "c%d_pc" % i in g:
+        pc, start, sel = g["c%d_pc" % i], g["c%d_start" % i], g["c%d_sel" % i]
+        p = cu(pc).requires_grad_(True)
+        out = utility.farthest_points_sample(p, sel.shape[2], start=cu(start))
+        assert np.array_equal(out.detach().cpu().numpy(), sel)
+        out.sum().backward()
+        assert float(p.grad.sum()) == pc.shape[0] * 3 * sel.shape[2]  # one unit per selected coordinate
+        i += 1
+    # random first picks: valid, distinct indices
+    r = utility.farthest_points_sample(cu(pc), 10)
+    assert r.shape == (pc.shape[0], 3, 10)
