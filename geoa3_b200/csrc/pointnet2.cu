@@ -408,8 +408,30 @@ group_points_kernel(const float* __restrict__ points, const int32_t* __restrict_
   const int cloud = blockIdx.z, c0 = blockIdx.y * GP_CC, cc = min(GP_CC, c - c0);
   const int tid = threadIdx.x;
   const float* src = points + ((size_t)cloud * c + c0) * n;
-  for (int i = tid; i < cc * n; i += GP_THREADS) s_rows[i] = src[i];
-  __syncthreads();
+  // The cc feature rows of this CTA are ONE contiguous block of cc*n floats: when it is 16-byte aligned and sized,
+  // a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) stages it — no per-thread load/store loop.
+  const unsigned bytes = (unsigned)(cc * n) * 4u;
+  __shared__ __align__(8) unsigned long long gp_bar;
+  const bool bulk = (bytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(src) & 15u) == 0u;
+  if (bulk) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&gp_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the init must be visible to the async proxy
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((unsigned)__cvta_generic_to_shared(s_rows)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    __syncthreads();  // everybody sees the initialised barrier before polling it
+    unsigned done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+    } while (!done);
+  } else {
+    for (int i = tid; i < cc * n; i += GP_THREADS) s_rows[i] = src[i];
+    __syncthreads();
+  }
   const int32_t* ix = idx + (size_t)cloud * E;
   float* dst = out + ((size_t)cloud * c + c0) * E;
   const int e_beg = blockIdx.x * GP_ETILE, e_end = min(E, e_beg + GP_ETILE);
