@@ -38,7 +38,7 @@ DEFAULTS = dict(
     attack_label="Untarget", classes=40, npoint=1024, binary_max_steps=10, initial_const=10.0, iter_max_steps=500,
     optim="adam", lr=0.01, eval_num=1, cls_loss_type="CE", confidence=0.0, dis_loss_type="CD", dis_loss_weight=1.0,
     is_cd_single_side=False, hd_loss_weight=0.1, curv_loss_weight=1.0, curv_loss_knn=16, uniform_loss_weight=0.0,
-    is_partial_var=False, is_subsample_opt=False, is_use_lr_scheduler=False, cc_linf=0.0, is_real_offset=False,
+    is_partial_var=False, knn_range=3, is_subsample_opt=False, is_use_lr_scheduler=False, cc_linf=0.0, is_real_offset=False,
     is_pro_grad=False, is_pre_jitter_input=False, is_debug=False)
 
 
@@ -157,14 +157,22 @@ class AttackState(object):
         self.last = {}
         if _get(cfg, "optim") == "adam":
             self.opt = torch.optim.Adam([self.offset], lr=_get(cfg, "lr"), capturable=True)
-        elif _get(cfg, "optim") == "sgd":
-            self.opt = torch.optim.SGD([self.offset], lr=_get(cfg, "lr"))
+        elif _get(cfg, "optim") == "sgd":  # the partial-variable branch uses momentum 0.9 (:250), the plain one none (:270)
+            self.opt = torch.optim.SGD([self.offset], lr=_get(cfg, "lr"),
+                                       momentum=0.9 if _get(cfg, "is_partial_var") else 0.0)
         else:
             raise AssertionError("Not support such optimizer.")
         self.gamma = 0.9990
         self.graph = None
         self.hints = loss_utils.HintBuffers()  # previous step's argmin / kNN indices seed the next search
-        self.subsample = bool(_get(cfg, "is_subsample_opt")) and n > _get(cfg, "npoint")
+        self.subsample = bool(_get(cfg, "is_subsample_opt")) and n > _get(cfg, "npoint") and not _get(cfg, "is_partial_var")
+        # --is_partial_var (:239-262, 279-280): only the knn_range nearest neighbours of a random seed point are
+        # variable; every 50 steps a new region is drawn, the perturbation so far is frozen into `base`
+        # (periodical_pc) and the optimiser starts afresh
+        self.partial = bool(_get(cfg, "is_partial_var"))
+        self.base = pc_ori
+        self.mask = None
+        self.host_step = 0
 
     def reset_global(self):
         """Back to the state of a fresh attack() call (used after the CUDA-graph warm-up/capture)."""
@@ -187,6 +195,8 @@ class AttackState(object):
             self.prev_constrain.fill_(1e10)
             self.step_idx.zero_()
             self.search_idx.fill_(search_step)
+            self.host_step = 0
+            self.base = self.pc_ori
             self.offset.copy_(init_offset)
             for st in self.opt.state.values():  # a fresh optimiser, in place (graph-safe)
                 for v in st.values():
@@ -198,7 +208,9 @@ class AttackState(object):
     def step(self):
         """One inner iteration (:238-368): forward, bookkeeping, losses, backward, optimiser step."""
         cfg = self.cfg
-        input_all = self.pc_ori + self.offset
+        if self.partial and self.host_step % 50 == 0:
+            self._new_region()
+        input_all = self.base + self.offset
         # --is_subsample_opt (:283-296): a cloud denser than the victim's input size is farthest-point subsampled
         # (fresh random first pick) for the forward of every step; the losses then compare that subsample with the
         # full original cloud, and success is a majority vote over `eval_num` independent subsamples
@@ -232,7 +244,10 @@ class AttackState(object):
             self.loss_log.index_copy_(0, self.step_idx.long().view(1), loss_n.detach()[None])
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
+        if self.partial:
+            self.offset.grad.mul_(self.mask)  # points outside the region are constants of this period
         self.opt.step()
+        self.host_step += 1
         with torch.no_grad():
             if _get(cfg, "is_pro_grad"):
                 if _get(cfg, "is_real_offset"):
@@ -243,6 +258,26 @@ class AttackState(object):
             self.step_idx.add_(1)
         self.last = dict(loss=loss.detach(), cls=cls_loss.detach(), dis=dis.detach(), hd=hd.detach(), curv=cu.detach(),
                          constrain=constrain.detach())
+
+    def _new_region(self):
+        """Start of a 50-step period of the partial-variable attack (eager only: host-side random seed point)."""
+        kr = int(_get(self.cfg, "knn_range"))
+        with torch.no_grad():
+            seed = int(np.random.randint(self.n))
+            q = self.pc_ori[:, :, seed:seed + 1].contiguous()
+            region = ops.knn(q, self.pc_ori, kr + 1)[0][:, 0, 1:].long()  # nearest one (the seed itself) dropped (:215)
+            if self.host_step > 0:
+                self.base = (self.base + self.offset).detach().clone()
+            sel = region[:, None, :].expand(self.b, 3, kr)
+            self.offset.zero_()
+            self.offset.scatter_(2, sel, torch.empty(self.b, 3, kr, device=self.offset.device).normal_(0.0, 1e-3))
+            self.mask = torch.zeros(self.b, 1, self.n, device=self.offset.device).scatter_(2, region[:, None, :], 1.0)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            for g in self.opt.param_groups:
+                g["lr"] = _get(self.cfg, "lr")
 
     # -- CUDA graph of one step
     def capture(self, warmup=3):
@@ -319,7 +354,7 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
 
     Extra keyword arguments (all optional): `global_batch` / `rows` describe the shard of a larger batch
     this process owns (loss scaling + initial offsets), `use_cuda_graph` replays the captured step."""
-    for flag in ("is_partial_var", "is_pre_jitter_input"):
+    for flag in ("is_pre_jitter_input",):
         if _get(cfg, flag):
             raise NotImplementedError("--%s is outside the B200 hot path (see DESIGN.md, out of scope)" % flag)
     device = device or torch.device("cuda", torch.cuda.current_device())
@@ -329,7 +364,7 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
     gb = global_batch if global_batch is not None else b
     st = AttackState(net, pc_ori, normal_ori, target, gt_target, cfg, targeted, global_batch=gb)
     steps = _get(cfg, "iter_max_steps")
-    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample  # (random first picks)
+    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample and not st.partial  # (host-side random picks)
     if graphable:
         st.begin_search_step(0, default_offsets(gb, n, 0, seed, rows).to(device))
         st.capture()

@@ -162,3 +162,31 @@ def test_attack_subsample_opt():
     L = np.asarray(losses)
     assert best.shape == (2, 3, 2048) and L.shape == (8, 2) and np.isfinite(L).all()
     assert not np.allclose(L[0], L[-1])
+
+
+def test_attack_partial_variable():
+    """--is_partial_var (geoA3_attack.py:239-262,279-280): only the knn_range neighbours of a random seed point move
+    in each 50-step period; earlier periods stay frozen in the accumulated cloud."""
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    b, n, kr = 3, 256, 3
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=60, curv_loss_knn=8, is_partial_var=True, knn_range=kr)
+    pc, nr, lab = synth.make_batch(b, n, 0)
+    dev = torch.device("cuda")
+    pc_t, nr_t, lab_t = torch.from_numpy(pc).to(dev), torch.from_numpy(nr).to(dev), torch.from_numpy(lab).to(dev)
+    st = atk.AttackState(net, pc_t, nr_t, lab_t, lab_t, cfg, targeted=False, global_batch=b)
+    np.random.seed(3)
+    st.begin_search_step(0, torch.zeros(b, 3, n, device=dev))
+    moved_after = {}
+    for i in range(60):
+        st.run_step()
+        if i in (49, 59):
+            moved_after[i] = ((st.base + st.offset - pc_t).abs().sum(1) > 0).sum(1).cpu().numpy()
+    assert (moved_after[49] == kr).all()                                  # first period: exactly the region
+    assert ((moved_after[59] >= kr) & (moved_after[59] <= 2 * kr)).all()  # second period adds a second region
+    assert np.isfinite(st.loss_log[:60].cpu().numpy()).all()
+    # the public entry point accepts the flag
+    out = atk.attack(net, _data(2, 256), atk.make_cfg(binary_max_steps=1, iter_max_steps=5, curv_loss_knn=8,
+                                                      is_partial_var=True))
+    assert out[0].shape == (2, 3, 256)
