@@ -38,8 +38,9 @@ DEFAULTS = dict(
     attack_label="Untarget", classes=40, npoint=1024, binary_max_steps=10, initial_const=10.0, iter_max_steps=500,
     optim="adam", lr=0.01, eval_num=1, cls_loss_type="CE", confidence=0.0, dis_loss_type="CD", dis_loss_weight=1.0,
     is_cd_single_side=False, hd_loss_weight=0.1, curv_loss_weight=1.0, curv_loss_knn=16, uniform_loss_weight=0.0,
-    is_partial_var=False, knn_range=3, is_subsample_opt=False, is_use_lr_scheduler=False, cc_linf=0.0, is_real_offset=False,
-    is_pro_grad=False, is_pre_jitter_input=False, is_debug=False)
+    is_partial_var=False, knn_range=3, is_subsample_opt=False, is_pre_jitter_input=False,
+    calculate_project_jitter_noise_iter=50, jitter_k=16, jitter_sigma=0.01, jitter_clip=0.05,
+    is_use_lr_scheduler=False, cc_linf=0.0, is_real_offset=False, is_pro_grad=False, is_debug=False)
 
 
 def make_cfg(**kw):
@@ -170,6 +171,7 @@ class AttackState(object):
         # variable; every 50 steps a new region is drawn, the perturbation so far is frozen into `base`
         # (periodical_pc) and the optimiser starts afresh
         self.partial = bool(_get(cfg, "is_partial_var"))
+        self.jitter_on, self.jitter = bool(_get(cfg, "is_pre_jitter_input")), None
         self.base = pc_ori
         self.mask = None
         self.host_step = 0
@@ -216,6 +218,14 @@ class AttackState(object):
         # full original cloud, and success is a majority vote over `eval_num` independent subsamples
         sub = self.subsample
         input_curr = utility.farthest_points_sample(input_all, _get(cfg, "npoint")) if sub else input_all
+        if self.jitter_on:
+            # --is_pre_jitter_input (:312-317,324-328): the forward sees the cloud plus a random tangent-plane jitter
+            # that is re-drawn every `calculate_project_jitter_noise_iter` steps; gradients reach the offset unchanged
+            if self.host_step % int(_get(cfg, "calculate_project_jitter_noise_iter")) == 0 or self.jitter is None \
+                    or self.jitter.shape != input_curr.shape:
+                self.jitter = utility.estimate_perpendicular(input_curr.detach(), int(_get(cfg, "jitter_k")),
+                                                             sigma=_get(cfg, "jitter_sigma"), clip=_get(cfg, "jitter_clip"))
+            input_curr = input_curr + self.jitter
         logits, loss, loss_n, cls_loss, dis, hd, cu, constrain = forward_step(
             self.net, self.pc_ori, input_curr, self.normal_ori, self.kappa_ori, self.target, self.scale_const, cfg,
             self.targeted, loss_divisor=self.global_batch, hints=loss_utils.NO_HINTS if sub else self.hints)
@@ -228,7 +238,8 @@ class AttackState(object):
                 success = hit.sum(1).to(torch.float32) > 0.5 * ev
                 pred = votes.mode(1).values
             else:
-                pred = logits.argmax(1)
+                # the reference judges success on the un-jittered cloud (:288-310 precede :312-317)
+                pred = (self.net(input_all.detach()) if self.jitter_on else logits).argmax(1)
                 success = _compare(pred, self.target, self.gt_target, self.targeted)
             metric = self.prev_constrain  # value of the previous step, as in the reference (:301 before :319)
             better = success & (metric < self.best_loss)
@@ -354,9 +365,6 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
 
     Extra keyword arguments (all optional): `global_batch` / `rows` describe the shard of a larger batch
     this process owns (loss scaling + initial offsets), `use_cuda_graph` replays the captured step."""
-    for flag in ("is_pre_jitter_input",):
-        if _get(cfg, flag):
-            raise NotImplementedError("--%s is outside the B200 hot path (see DESIGN.md, out of scope)" % flag)
     device = device or torch.device("cuda", torch.cuda.current_device())
     targeted = _get(cfg, "attack_label") != "Untarget"
     pc_ori, normal_ori, target, gt_target = _unpack(input_data, cfg, device)
@@ -364,7 +372,7 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
     gb = global_batch if global_batch is not None else b
     st = AttackState(net, pc_ori, normal_ori, target, gt_target, cfg, targeted, global_batch=gb)
     steps = _get(cfg, "iter_max_steps")
-    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample and not st.partial  # (host-side random picks)
+    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample and not st.partial and not st.jitter_on  # (host-side random picks / periods)
     if graphable:
         st.begin_search_step(0, default_offsets(gb, n, 0, seed, rows).to(device))
         st.capture()

@@ -231,3 +231,33 @@ def ref_farthest_points_sample(points, num_points, start):
         return ns["farthest_points_sample"](torch.from_numpy(np.asarray(points, np.float32)), num_points).numpy()
     finally:
         torch.randint, torch.Tensor.cuda = saved
+
+
+def ref_utility_functions(names):
+    """Compiles the named top-level functions of the reference's Lib/utility.py IN PLACE (AST nodes; the module
+    itself cannot be imported) into a namespace that provides the pytorch3d stub, an identity `.cuda()` (applied
+    by the caller) and `torch.symeig` (removed from torch >= 1.13) as torch.linalg.eigh."""
+    import ast
+
+    path = osp.join(REF_ROOT, "Lib", "utility.py")
+    tree = ast.parse(open(path).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    ns = {"torch": torch, "np": np, "knn_points": lambda p1, p2, K=1, **kw: _knn_points(p1, p2, K=K),
+          "knn_gather": _knn_gather}
+    exec(compile(ast.Module(fns, []), path, "exec"), ns)
+    return ns
+
+
+def ref_estimate_normal(pc, k):
+    """Reference estimate_normal (Lib/utility.py:40-90) on CPU -> [b,3,n]."""
+    ns = ref_utility_functions(["estimate_normal"])
+    had = hasattr(torch, "symeig")
+    saved = getattr(torch, "symeig", None)
+    torch.symeig = lambda A, eigenvectors=True: torch.linalg.eigh(A)
+    try:
+        return ns["estimate_normal"](torch.from_numpy(np.asarray(pc, np.float32)), k).numpy()
+    finally:
+        if had:
+            torch.symeig = saved
+        else:
+            del torch.symeig

@@ -23,6 +23,7 @@ CASES = [
     ("loss_b2_n500_k8", 2, 500, 8, 1e-3, 3),     # ragged n, reference-sized initial perturbation
     ("loss_b4_n128_k16_big", 4, 128, 16, 1e-1, 6),  # large perturbation: many-to-one argmins, empty columns
 ]
+NORMAL_CASES = [(3, 512, 16), (2, 300, 8)]   # b, n, k
 FPS_CASES = [(3, 2048, 256), (2, 1000, 100), (1, 5000, 64), (2, 300, 300)]   # b, n, picks
 DEFENSE_CASES = [  # n, outlier_knn, alpha, drop_num, offset std
     (1024, 2, 1.1, 50, 1e-2),
@@ -35,7 +36,7 @@ AUX_CASES = [
 ]
 
 
-def main(which=("loss", "aux", "defense", "fps")):
+def main(which=("loss", "aux", "defense", "fps", "normal")):
     torch.manual_seed(0)
     torch.set_num_threads(4)
     for name, b, n, k, std, start in (CASES if "loss" in which else []):
@@ -88,6 +89,16 @@ def main(which=("loss", "aux", "defense", "fps")):
             print("fps case", i, out["c%d_sel" % i].shape)
         np.savez_compressed(osp.join(HERE, "fps_plain_cases.npz"), **out)
 
+    # estimate_normal (Lib/utility.py:40-90) — neighbourhood PCA normals
+    if "normal" in which:
+        out = {}
+        for i, (b, n, k) in enumerate(NORMAL_CASES):
+            pc, _, _ = synth.make_batch(b, n, 2 * i)
+            out["c%d_pc" % i], out["c%d_k" % i] = pc, np.int32(k)
+            out["c%d_normal" % i] = ref_loader.ref_estimate_normal(pc, k)
+            print("normal case", i, out["c%d_normal" % i].shape)
+        np.savez_compressed(osp.join(HERE, "estimate_normal_cases.npz"), **out)
+
 
 if __name__ == "__main__":
-    main(tuple(sys.argv[1:]) or ("loss", "aux", "defense", "fps"))   # e.g. `make_golden.py aux` regenerates only aux_*
+    main(tuple(sys.argv[1:]) or ("loss", "aux", "defense", "fps", "normal"))   # e.g. `make_golden.py aux` regenerates only aux_*

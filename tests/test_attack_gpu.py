@@ -190,3 +190,16 @@ def test_attack_partial_variable():
     out = atk.attack(net, _data(2, 256), atk.make_cfg(binary_max_steps=1, iter_max_steps=5, curv_loss_knn=8,
                                                       is_partial_var=True))
     assert out[0].shape == (2, 3, 256)
+
+
+def test_attack_pre_jitter_input():
+    """--is_pre_jitter_input: tangent-plane jitter re-drawn every few steps, success judged on the clean cloud."""
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=7, curv_loss_knn=8, is_pre_jitter_input=True,
+                       calculate_project_jitter_noise_iter=3, jitter_k=8)
+    torch.manual_seed(2)
+    out = atk.attack(net, _data(3, 256), cfg)
+    L = np.asarray(out[4])
+    assert out[0].shape == (3, 3, 256) and L.shape == (7, 3) and np.isfinite(L).all()

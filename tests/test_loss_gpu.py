@@ -495,3 +495,40 @@ def test_backward_large_clouds():
             os.environ.pop("GEOA3_BWD_LARGE", None)
         L.clear_cache()
     assert torch.equal(grads[0], grads[1])
+
+
+def test_pca_estimators_vs_reference_golden():
+    """estimate_normal / estimate_perpendicular / estimate_normal_via_ori_normal (Lib/utility.py:40-149) on the CUDA
+    neighbour search.  Normals vs the reference function executed in place (fixture), compared up to sign — the
+    reference's own orientation rule reads rounding noise — and allowing the few points whose two smallest
+    eigenvalues nearly coincide; the jitter must lie in the tangent plane and respect the clip."""
+    import os.path as osp
+
+    from geoa3_b200 import utility as U
+    from helpers import GOLDEN_DIR
+
+    g = np.load(osp.join(GOLDEN_DIR, "estimate_normal_cases.npz"))
+    i = 0
+    while "c%d_pc" % i in g:
+        pc, k, ref = g["c%d_pc" % i], int(g["c%d_k" % i]), g["c%d_normal" % i]
+        got = U.estimate_normal(cu(pc), k).cpu().numpy()
+        assert got.shape == ref.shape
+        # the reference's sign rule is -sign(sum of centred neighbours . normal): rounding noise, and exactly 0 (a
+        # zero "normal") wherever that sum cancels exactly — on either side, at different points
+        live = (np.linalg.norm(got, axis=1) > 0.5) & (np.linalg.norm(ref, axis=1) > 0.5)
+        assert live.mean() > 0.8
+        cos = np.abs((got * ref).sum(1))[live]
+        assert np.mean(cos > 0.999) > 0.97 and np.median(cos) > 0.99999, (np.mean(cos > 0.999), np.median(cos))
+        torch.manual_seed(0)
+        jit = U.estimate_perpendicular(cu(pc), k, sigma=0.01, clip=0.05).cpu().numpy()
+        assert jit.shape == pc.shape and np.abs(jit).max() <= 0.1 + 1e-6
+        along = (np.abs((jit * got).sum(1)) / (np.linalg.norm(jit, axis=1) + 1e-12))[live]
+        assert np.median(along) < 1e-3                    # tangent-plane noise: no component along the normal
+        i += 1
+    assert i == 2
+    pc, nr, _ = synth.make_batch(2, 400, 0)
+    same = U.estimate_normal_via_ori_normal(cu(pc), cu(pc), cu(nr), 3)
+    assert torch.equal(same, cu(nr))                       # unmoved points take the original normal itself
+    moved = pc + synth.make_offsets(2, 400, std=2e-2)
+    est = U.estimate_normal_via_ori_normal(cu(moved), cu(pc), cu(nr), 3).cpu().numpy()
+    assert np.allclose(np.linalg.norm(est, axis=1), 1.0, atol=1e-4) and np.median(np.abs((est * nr).sum(1))) > 0.95
