@@ -203,3 +203,31 @@ def test_attack_pre_jitter_input():
     out = atk.attack(net, _data(3, 256), cfg)
     L = np.asarray(out[4])
     assert out[0].shape == (3, 3, 256) and L.shape == (7, 3) and np.isfinite(L).all()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(cls_loss_type="Margin", attack_label="All", confidence=0.5),
+    dict(dis_loss_type="L2", hd_loss_weight=0.0, curv_loss_weight=0.0),
+    dict(is_pro_grad=True, is_real_offset=True, cc_linf=0.02),
+    dict(optim="sgd", is_use_lr_scheduler=True),
+    dict(is_cd_single_side=True, cls_loss_type="None"),
+], ids=["margin_targeted", "l2_only", "projected_clipped", "sgd_scheduler", "single_side_no_cls"])
+def test_attack_flag_matrix(kw):
+    """Every remaining flag combination of the point-cloud attack loop runs to finite losses (and, where the step is
+    graph-capturable, the replay equals the eager run)."""
+    from geoa3_b200 import attack as atk
+
+    net = _net()
+    cfg = atk.make_cfg(binary_max_steps=2, iter_max_steps=4, curv_loss_knn=8, **kw)
+    data = _data(3, 256)
+    if kw.get("attack_label") == "All":
+        data = data + [torch.tensor([[5], [7], [9]])]
+    out = atk.attack(net, data, cfg, use_cuda_graph=True)
+    L = np.asarray(out[4])
+    assert L.shape == (4, 3) and np.isfinite(L).all()
+    if not kw.get("is_use_lr_scheduler"):
+        Le = np.asarray(atk.attack(net, data, cfg, use_cuda_graph=False)[4])
+        assert np.allclose(L, Le, rtol=1e-4, atol=1e-5)
+    if "cc_linf" in kw:
+        assert float((out[0] - torch.from_numpy(synth.make_batch(3, 256)[0]).cuda()).abs().max()) <= 0.02 + 1e-6 \
+            or not out[2].any()
