@@ -25,6 +25,18 @@ namespace geoa3 {
 // ============================================================================ FPS
 constexpr int FPS_MAX_WARPS = 32;
 
+// Distance used by the sampling kernels.  MODE 0: the pointnet2 squared distance (y,x,z contraction).  MODE 1/2: the
+// Euclidean NORM of Lib/utility.py:183 (`torch.norm(diff, dim=1)`): sqrt of the sum of squares, accumulated as an
+// fma chain in x,y,z order (1) or as separately rounded squares (2) — the arg-max (and its ties) is then taken on
+// the same rounded values the reference compares.
+template <int MODE>
+__device__ __forceinline__ float fps_dist(float px, float py, float pz, float qx, float qy, float qz) {
+  if constexpr (MODE == 0) return dist2_pn2(px, py, pz, qx, qy, qz);
+  const float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+  if constexpr (MODE == 1) return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+  return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
 // reference block size: opt_n_threads(n) = clamp(2^floor(log2 n), 1, 512) (cuda_utils.h:13-19)
 static int ref_fps_block(int n) {
   int p = 1;
@@ -32,7 +44,7 @@ static int ref_fps_block(int n) {
   return p;
 }
 
-template <int P>
+template <int P, int MODE>
 __global__ void __launch_bounds__(1024)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs,
            const int32_t* __restrict__ start) {
@@ -75,7 +87,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits
     float hmax = 0.f;
 #pragma unroll
     for (int t = 0; t < P; ++t) {
-      const float d = dist2_pn2(px[t], py[t], pz[t], x1, y1, z1);
+      const float d = fps_dist<MODE>(px[t], py[t], pz[t], x1, y1, z1);
       temp[t] = fminf(d, temp[t]);
       hmax = fmaxf(hmax, tk[t] != 0u ? temp[t] : 0.f);  // distances are >= +0: float order == bit order
     }
@@ -187,7 +199,7 @@ fps_warp_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref
 // search), and the 4 warp partials are merged through a double-buffered shared slot with ONE barrier per round.
 constexpr int FPSQ_WARPS = 4;
 
-template <int P>
+template <int P, int MODE>
 __global__ void __launch_bounds__(FPSQ_WARPS * 32)
 fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref_bits, int32_t* __restrict__ idxs,
                 const int32_t* __restrict__ start) {
@@ -231,7 +243,13 @@ fps_quad_kernel(const float* __restrict__ xyz, int n, int m, int ref_bs, int ref
     float hm[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      const float2 d = dist2x2_pn2(px[h], py[h], pz[h], nx, ny, nz);
+      float2 d;
+      if constexpr (MODE == 0) {
+        d = dist2x2_pn2(px[h], py[h], pz[h], nx, ny, nz);
+      } else {
+        d.x = fps_dist<MODE>(px[h].x, py[h].x, pz[h].x, -x1, -y1, -z1);
+        d.y = fps_dist<MODE>(px[h].y, py[h].y, pz[h].y, -x1, -y1, -z1);
+      }
       temp[h].x = fminf(d.x, temp[h].x);  // frozen / padding points sit at 0 forever
       temp[h].y = fminf(d.y, temp[h].y);
       hm[h] = fmaxf(temp[h].x, temp[h].y);
@@ -1030,6 +1048,35 @@ using namespace geoa3;
 
 // start == nullptr: pointnet2 semantics (first pick 0, frozen points, reference tie order);
 // start != nullptr: plain FPS from the given first picks (Lib/utility.py:175-187)
+template <int MODE>
+static int launch_fps(const float* xyz, int b, int n, int m, const int32_t* start, int32_t* idx, size_t smem, int bs,
+                      int bits, cudaStream_t s) {
+  const bool one_warp = !start && getenv("GEOA3_FPS_WARP") != nullptr;  // A/B knob for tools/time_kernels.py, not part of the API
+  if (one_warp && n <= 512) {
+    fps_warp_kernel<16><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (one_warp && n <= 1024) {
+    fps_warp_kernel<32><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
+  } else if (n <= 256) {
+    fps_quad_kernel<2, MODE><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else if (n <= 512) {
+    fps_quad_kernel<4, MODE><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else if (n <= 1024) {
+    fps_quad_kernel<8, MODE><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else if (n <= 2048) {
+    fps_quad_kernel<16, MODE><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else if (n <= 4096) {
+    const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
+    fps_kernel<4, MODE><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else if (n <= 8192) {
+    fps_kernel<8, MODE><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else if (n <= 16384) {
+    fps_kernel<16, MODE><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx, start);
+  } else {
+    return GEOA3_EUNSUPPORTED;
+  }
+  return GEOA3_LAUNCH_RESULT();
+}
+
 static int run_fps(const float* xyz, int b, int n, int m, const int32_t* start, int32_t* idx, geoa3_stream_t stream) {
   GEOA3_CHECK_ARG(xyz && idx && b > 0 && n > 0 && m > 0);
   if (n >= (1 << 20) || (size_t)n * 12 > 200 * 1024) return GEOA3_EUNSUPPORTED;
@@ -1041,36 +1088,23 @@ static int run_fps(const float* xyz, int b, int n, int m, const int32_t* start, 
   if (start) bits = 0;  // ties -> lowest index
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fps_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaSuccess;
+#define GEOA3_FPS_ATTR(P_, M_) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<P_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+    GEOA3_FPS_ATTR(4, 0); GEOA3_FPS_ATTR(8, 0); GEOA3_FPS_ATTR(16, 0);
+    GEOA3_FPS_ATTR(4, 1); GEOA3_FPS_ATTR(8, 1); GEOA3_FPS_ATTR(16, 1);
+    GEOA3_FPS_ATTR(4, 2); GEOA3_FPS_ATTR(8, 2); GEOA3_FPS_ATTR(16, 2);
+#undef GEOA3_FPS_ATTR
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  const bool one_warp = !start && getenv("GEOA3_FPS_WARP") != nullptr;  // A/B knob for tools/time_kernels.py, not part of the API
-  if (one_warp && n <= 512) {
-    fps_warp_kernel<16><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
-  } else if (one_warp && n <= 1024) {
-    fps_warp_kernel<32><<<b, 32, smem, s>>>(xyz, n, m, bs, bits, idx);
-  } else if (n <= 256) {
-    fps_quad_kernel<2><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else if (n <= 512) {
-    fps_quad_kernel<4><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else if (n <= 1024) {
-    fps_quad_kernel<8><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else if (n <= 2048) {
-    fps_quad_kernel<16><<<b, FPSQ_WARPS * 32, smem + (size_t)m * 4, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else if (n <= 4096) {
-    const int T = min(1024, max(32, ((n + 3) / 4 + 31) & ~31));
-    fps_kernel<4><<<b, T, smem, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else if (n <= 8192) {
-    fps_kernel<8><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else if (n <= 16384) {
-    fps_kernel<16><<<b, 1024, smem, s>>>(xyz, n, m, bs, bits, idx, start);
-  } else {
-    return GEOA3_EUNSUPPORTED;
-  }
-  return GEOA3_LAUNCH_RESULT();
+  // norm arithmetic of the plain variant: separately rounded squares — what torch's CUDA norm reduction computes
+  // (tools/time_kernels.py --fps-plain: picks identical to the torch loop; GEOA3_FPS_NORM=1 selects the fma chain,
+  // which diverges from it at near-ties)
+  const char* nm = getenv("GEOA3_FPS_NORM");
+  if (!start) return launch_fps<0>(xyz, b, n, m, start, idx, smem, bs, bits, s);
+  if (nm && atoi(nm) == 1) return launch_fps<1>(xyz, b, n, m, start, idx, smem, bs, bits, s);
+  return launch_fps<2>(xyz, b, n, m, start, idx, smem, bs, bits, s);
 }
 
 extern "C" int geoa3_furthest_point_sampling(const float* xyz, int b, int n, int m, int32_t* idx,

@@ -139,9 +139,9 @@ GEOA3_API int geoa3_furthest_point_sampling(const float *xyz, int b, int n, int 
 /* Plain farthest point sampling from a given first pick per cloud: start[b] (int32, clamped to [0,n)), no frozen
  * points, running minimum from +inf, arg-max ties -> lowest index; idx[b][m] int32 with idx[.][0] = start.
  * Replaces: farthest_points_sample, Lib/utility.py:175-187 (a Python loop of m-1 torch.min / argmax passes), the
- * per-iteration subsampling of --is_subsample_opt (Attacker/geoA3_attack.py:283-292).  Squared distances (same
- * fp32 chain as the other sampling kernels) instead of the reference's norm: same pick except where sqrt
- * rounding merges two different squared distances. */
+ * per-iteration subsampling of --is_subsample_opt (Attacker/geoA3_attack.py:283-292).  Distances are Euclidean
+ * norms like the reference's (`torch.norm`, :183): sqrt.rn of (dx*dx + dy*dy) + dz*dz with separately rounded
+ * products, the arithmetic of torch's CUDA norm reduction, so rounding ties fall the same way. */
 GEOA3_API int geoa3_farthest_points_sample(const float *xyz, int b, int n, int m, const int32_t *start, int32_t *idx,
                                            geoa3_stream_t stream);
 

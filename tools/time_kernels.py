@@ -61,6 +61,33 @@ def sweep():
                                   fp32_tflops_hinted=round(flop / (t_hint[0] * 1e-6) / 1e12, 2))))
 
 
+def fps_plain():
+    """farthest_points_sample (Lib/utility.py:175-187): one launch here vs the reference's loop of num_points-1 torch
+    passes (restated with plain torch ops and run on the same GPU)."""
+    from geoa3_b200 import utility
+
+    def torch_loop(pts, m, start):
+        b, _, n = pts.shape
+        sel = start.long()[:, None]
+        dists = torch.full((b, n), float("inf"), device=pts.device)
+        for _ in range(m - 1):
+            last = torch.gather(pts, 2, sel[:, -1][:, None, None].expand(b, 3, 1))
+            dists = torch.min(dists, torch.norm(pts - last, dim=1))
+            sel = torch.cat([sel, torch.argmax(dists, dim=1, keepdim=True)], dim=1)
+        return torch.gather(pts, 2, sel[:, None, :].expand(b, 3, m))
+
+    for (b, n, m) in ((64, 4096, 1024), (64, 10000, 1024), (250, 2048, 1024)):
+        pc, _, _ = synth.make_batch(8, n)
+        pts = torch.from_numpy(np.tile(pc, ((b + 7) // 8, 1, 1))[:b].copy()).cuda()
+        start = torch.randint(n, (b,), device="cuda", dtype=torch.int32)
+        ours = utility.farthest_points_sample(pts, m, start=start)
+        ref = torch_loop(pts, m, start)
+        t_o = timeit(lambda: utility.farthest_points_sample(pts, m, start=start), iters=5, warm=2)
+        t_r = timeit(lambda: torch_loop(pts, m, start), iters=2, warm=1)
+        print(json.dumps(dict(what="farthest_points_sample", b=b, n=n, m=m, ours_us=round(t_o[0], 1),
+                              torch_loop_us=round(t_r[0], 1), same_picks=bool(torch.equal(ours, ref)))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--b", type=int, default=250)
@@ -68,9 +95,12 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--pn2", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config[3]: curvature-loss scaling sweep")
+    ap.add_argument("--fps-plain", dest="fps_plain", action="store_true", help="farthest_points_sample vs the torch loop")
     a = ap.parse_args()
     if a.sweep:
         return sweep()
+    if a.fps_plain:
+        return fps_plain()
     b, n, k = a.b, a.n, a.k
     pc, nr, _ = synth.make_batch(min(b, 20), n)
     reps = (b + pc.shape[0] - 1) // pc.shape[0]
