@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — GeoA3 attack-iteration throughput on B200 (BASELINE.json metric, config[1]).
+"""bench.py — GeoA3 attack-iteration throughput on B200 (BASELINE.json metric; headline = config[1]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--arch PointNet]
 
@@ -7,13 +7,26 @@ A "step" is ONE attack iteration (Attacker/geoA3_attack.py:238-368 of the refere
 B=250 synthetic ModelNet-shaped instances (N=1024 points, random-init PointNet(40) in eval mode,
 untargeted CE + 10*(1.0*CD + 0.1*HD + 1.0*curvature k=16), Adam lr 0.01): victim forward, fused
 Chamfer/Hausdorff/curvature losses, backward to the offset, Adam update, success bookkeeping — replayed
-as one CUDA graph.  Every GPU owns its own 250-instance batch (weak scaling, no data-path collective);
-value = N_gpus * K / max-over-ranks device time.
+as one CUDA graph.
 
-Printed JSON (one line, rank 0): see the task contract; extra keys `roofline` (dominant own kernel,
-measured live), `cpu_baseline` (oracle port of the same step on the host cores, bounded sample),
-`loss_fwd_bwd_us` (per-kernel CUDA-event times of the loss path at the bench batch).
-`--impl reference` times the CPU port of the reference path (kind "port") on all host cores.
+Headline (`value`, unchanged since round 1): every GPU owns its own 250-instance batch (weak scaling, no
+data-path collective); value = N_gpus * K / max-over-ranks device time.
+
+Sub-records of the same JSON line (rank 0 prints ONE line):
+  strong      config[1] as the north star states it: ONE 250-instance batch sharded by instance over the N
+              ranks (geoa3_b200.dist), K steps per rank + the final NCCL all-gather of the per-instance
+              statistics, device time max over ranks.
+  strong_msg  config[4]: PointNet++ MSG, 2 000 instances sharded over the N ranks (micro-batches of 250 per
+              rank, one captured step reused through AttackState.load_batch), + the final all-gather.
+  configs     (N=1 only) config[2] PointNet++ SSG step with every own op timed beside the reference's kernel
+              recompiled for sm_100 (oracle/_ref, baseline leg) and its HBM-roofline fraction; config[3] the
+              curvature-loss sweep (B=64, N=1024/4096/10000, k=16/32).
+  loss_fwd_bwd_us / gpu_reference_loss_us   own loss-path kernels vs the dense-torch loss the reference documents
+              (Lib/loss_utils.py:30-31,54-56,67-69) on the same B200.
+  roofline    dominant own kernel of the loss path, measured live.
+  cpu_baseline  the oracle port of the same step on the host cores: ONE real step of all 250 instances
+              (chunks of 25), plus config[0] (b=1, 10 iterations, loss-only and with PointNet).
+`--impl reference` runs the CPU port for real at B=250 (reduced step count, reported as run).
 """
 import argparse
 import json
@@ -34,7 +47,8 @@ import torch  # noqa: E402
 METRIC = "geoa3_attack_iters_per_s"
 UNIT = "attack-iters/s (one iter = one Adam step of a 250-instance batch; whole job, all GPUs)"
 B_PER_GPU, NPTS, KNN = 250, 1024, 16
-CPU_SAMPLE_B = 4
+MSG_TOTAL, MSG_MICRO = 2000, 250
+CPU_CHUNK = 25
 
 
 def parse():
@@ -47,6 +61,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + strong only (skip configs[2..4], baselines)")
+    ap.add_argument("--msg-total", type=int, default=MSG_TOTAL)
     return ap.parse_args()
 
 
@@ -129,41 +145,6 @@ def time_events(fn, iters, warm):
     return sum(ts) / len(ts)
 
 
-def kernel_breakdown(pc_ori, nrm, adv, k):
-    """CUDA-event time of each own kernel of the loss path at the bench batch (µs, mean of 10), in the exact
-    configuration the attack step launches them: 1-NN seeded and kNN threshold hinted with the previous
-    step's indices (here: the indices of a cloud one Adam step away)."""
-    from geoa3_b200 import ops
-
-    b, _, n = adv.shape
-    prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
-    _, hj, _, hi = ops.nn_pair(prev, pc_ori)
-    hn = ops.knn(prev, prev, k + 1, drop=1)[0]
-    perm, iperm = ops.visit_order(pc_ori)  # once per attack in the real driver (HintBuffers.ensure_order)
-    nnkw = dict(hint_a2o=hj, hint_o2a=hi, perm_a=perm, perm_o=perm, iperm_a=iperm, iperm_o=iperm,
-                ori_arranged=ops.arrange(pc_ori, perm))
-    d1, js, d2, is_ = ops.nn_pair(adv, pc_ori, **nnkw)
-    nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
-    nbr_o = ops.knn(pc_ori, pc_ori, k + 1, drop=1)[0]
-    ko = ops.kappa_loss_fwd(pc_ori, normal=nrm, nbr=nbr_o)["kappa"]
-
-    def fwd():
-        return ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr, d_a2o=d1, d_o2a=d2, kappa_ori=ko, want_nrm=True,
-                                  want_cd=True, want_hd=True, want_curv=True)
-
-    out = fwd()
-    g = torch.full((b,), 1.0 / b, device=adv.device)
-    t = {
-        "nn_pair": time_events(lambda: ops.nn_pair(adv, pc_ori, **nnkw), 10, 3),  # incl. the launch arranging adv
-        "knn": time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), 10, 3),
-        "kappa_loss_fwd": time_events(fwd, 10, 3),
-        "loss_bwd": time_events(lambda: ops.loss_bwd(adv, ori=pc_ori, nrm_adv=out["nrm"], kappa_adv=out["kappa"],
-                                                     kappa_ori=ko, jstar=js, istar=is_, nbr=nbr, hd_arg=out["hd_arg"],
-                                                     g_cd=g, g_hd=g, g_cu=g), 10, 3),
-    }
-    return {k_: round(v, 2) for k_, v in t.items()}
-
-
 def peaks():
     p = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
     f = osp.join(ROOT, "MEASURED_PEAKS.json")
@@ -176,37 +157,302 @@ def peaks():
     return p
 
 
-def cpu_baseline(steps, warmup, arch):
-    """Oracle port of the same attack step on the host cores, bounded sample of CPU_SAMPLE_B instances."""
+def ncu_traffic():
+    """DRAM bytes per launch of the own loss kernels from the committed `ncu --set full` capture of this round
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at B=250, N=1024, k=16)."""
+    f = osp.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(f))
+    except Exception:
+        return {}
+
+
+def build_state(arch, b, n, row0, global_batch, dev, rows=None, graph=True):
+    """Victim + AttackState for rows [row0, row0+b) of a `global_batch`-row attack, step captured."""
+    from geoa3_b200 import attack as atk
+    from geoa3_b200.victims import build_victim
+
+    torch.manual_seed(0)
+    net = build_victim(arch).to(dev).eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    pc_h, nr_h, lab_h = make_inputs(b, n, row0)
+    pc_pin, nr_pin = torch.from_numpy(pc_h).pin_memory(), torch.from_numpy(nr_h).pin_memory()
+    off_pin = atk.default_offsets(global_batch, n, 0, 0, rows if rows is not None else range(row0, row0 + b)).pin_memory()
+    target = torch.from_numpy(lab_h).to(dev)
+    cfg = atk.make_cfg(attack_label="Untarget", curv_loss_knn=KNN)
+    st = atk.AttackState(net, pc_pin.to(dev), nr_pin.to(dev), target, target, cfg, targeted=False,
+                         global_batch=global_batch)
+    st.begin_search_step(0, off_pin.to(dev))
+    return st, (pc_pin, nr_pin, off_pin)
+
+
+def count_and_capture(st, off_dev, graph=True):
+    from geoa3_b200 import ops
+
+    st.step()          # the first step also pays the one-time arrangement of the original cloud
+    ops.LAUNCHES = 0
+    st.step()
+    launches = ops.LAUNCHES
+    if graph:
+        st.capture()
+    st.reset_global()
+    st.begin_search_step(0, off_dev)
+    return launches
+
+
+def timed_steps(st, steps, warmup, dev, gdist, tail=None):
+    """W warm-up + K timed steps (+ optional tail() inside the timed region); device time, max over ranks (ms)."""
+    for _ in range(warmup):
+        st.run_step()
+    torch.cuda.synchronize()
+    gdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        st.run_step()
+    out = tail() if tail is not None else None
+    e1.record()
+    torch.cuda.synchronize()
+    gdist.barrier()
+    return gdist.max_over_ranks(e0.elapsed_time(e1), dev), out
+
+
+# ------------------------------------------------------------------ loss-path kernels
+def kernel_breakdown(pc_ori, nrm, adv, k):
+    """CUDA-event time of each own kernel of the loss path at the bench batch (µs, mean of 10), in the exact
+    configuration the attack step launches them (loss_utils._GeoLoss with HintBuffers): 1-NN seeded and slab-arranged,
+    kNN hinted with the previous step's neighbours (here: of a cloud one Adam step away)."""
+    from geoa3_b200 import loss_utils as L
+    from geoa3_b200 import ops
+
+    b, _, n = adv.shape
+    prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
+    hb = L.HintBuffers()
+    ko = L._get_kappa_ori(pc_ori, nrm, k).detach()
+    plan = L.step_plan(prev, pc_ori, nrm, ko, k, hb)      # fills the hint buffers from the previous cloud
+    plan = L.step_plan(adv, pc_ori, nrm, ko, k, hb)       # the calls of one steady-state step, as closures
+    g = torch.full((b,), 1.0 / b, device=adv.device)
+    t = {}
+    for name, fn in plan["launches"](g):
+        t[name] = time_events(fn, 10, 3)
+    return {k_: round(v, 2) for k_, v in t.items()}
+
+
+def dense_torch_loss_us(pc_ori, nrm, adv, k):
+    """The GPU "reference kernel" bar of BASELINE.md section 3(i): the dense-torch formulation the reference documents
+    next to every pytorch3d call (Lib/loss_utils.py:30-31,54-56,67-69: [b,n,n] squared distances + topk), forward +
+    backward of CD + 0.1*HD + curvature on the same B200, plain torch ops (restated here; nothing from oracle/)."""
+    b, _, n = adv.shape
+    chunk = 50  # [chunk,n,n] matrices: the full batch at once would need > 10 GB of temporaries
+
+    def knn_dense(p1, p2, K):
+        d = ((p1.unsqueeze(3) - p2.unsqueeze(2)) ** 2).sum(1)
+        return torch.topk(d, K, dim=2, largest=False, sorted=True)
+
+    def kappa(pc, normal):
+        bb = pc.shape[0]
+        idx = knn_dense(pc, pc, k + 1)[1][:, :, 1:].contiguous()
+        nn_pts = torch.gather(pc, 2, idx.view(bb, 1, n * k).expand(bb, 3, n * k)).view(bb, 3, n, k)
+        v = nn_pts - pc.unsqueeze(3)
+        v = v / v.norm(2, 1, keepdim=True).clamp(min=1e-12)
+        return torch.abs((v * normal.unsqueeze(3)).sum(1)).mean(2)
+
+    ko = torch.cat([kappa(pc_ori[i:i + chunk], nrm[i:i + chunk]) for i in range(0, b, chunk)])
+
+    def run():
+        for i in range(0, b, chunk):
+            a = adv[i:i + chunk].detach().requires_grad_(True)
+            o, nn_, kk = pc_ori[i:i + chunk], nrm[i:i + chunk], ko[i:i + chunk]
+            bb = a.shape[0]
+            d1, j1 = knn_dense(a, o, 1)
+            d2, _ = knn_dense(o, a, 1)
+            cd = d1.squeeze(-1).mean(-1) + d2.squeeze(-1).mean(-1)
+            hd = d1.squeeze(-1).max(-1)[0]
+            normal = torch.gather(nn_, 2, j1.view(bb, 1, n).expand(bb, 3, n))
+            cu = ((kappa(a, normal) - torch.gather(kk, 1, j1.squeeze(-1))) ** 2).mean(-1)
+            (cd + 0.1 * hd + cu).sum().backward()
+
+    return round(time_events(run, 3, 1), 1)
+
+
+# ------------------------------------------------------------------ config[2]: PointNet++ SSG ops
+def ssg_ops_record(b, dev):
+    """Own pointnet2 ops at the SSG shapes (Model/PointNetPP_ssg.py:65-87) with their HBM-roofline fraction, and the
+    reference's kernels recompiled for sm_100 (oracle/_ref — baseline leg only) timed beside them."""
+    from geoa3_b200 import ops
+
+    pk = peaks()
+    pc_h, _, _ = make_inputs(b, NPTS, 0)
+    ori = torch.from_numpy(pc_h).to(dev)
+    xyz = ori.transpose(1, 2).contiguous()
+    fi = ops.furthest_point_sampling(xyz, 512)
+    new = ops.gather_points(ori, fi).transpose(1, 2).contiguous()
+    idx = ops.ball_query(new, xyz, 0.2, 64)
+    fi2 = ops.furthest_point_sampling(new, 128)
+    new2 = ops.gather_points(new.transpose(1, 2).contiguous(), fi2).transpose(1, 2).contiguous()
+    idx2 = ops.ball_query(new2, new, 0.4, 64)
+    feats = torch.randn(b, 128, 512, device=dev)
+    go = torch.randn(b, 128, 128, 64, device=dev)
+    go3 = torch.randn(b, 3, 512, 64, device=dev)
+    n, m1, m2, ns = NPTS, 512, 128, 64
+
+    def grp(c, nn_, m):  # SURVEY section 8d: 4*C*n + 4*m*ns + 4*C*m*ns per cloud
+        return b * (4 * c * nn_ + 4 * m * ns + 4 * c * m * ns)
+
+    cases = [
+        ("fps_1024_512", lambda e: e.furthest_point_sampling(xyz, 512), b * (12 * n + 4 * m1)),
+        ("fps_512_128", lambda e: e.furthest_point_sampling(new, 128), b * (12 * m1 + 4 * m2)),
+        ("gather_3_512", lambda e: e.gather_points(ori, fi), b * 28 * m1),
+        ("ball_query_r.2_ns64", lambda e: e.ball_query(new, xyz, 0.2, 64), b * (12 * m1 + 12 * n + 4 * m1 * ns)),
+        ("ball_query_r.4_ns64", lambda e: e.ball_query(new2, new, 0.4, 64), b * (12 * m2 + 12 * m1 + 4 * m2 * ns)),
+        ("group_c3_m512", lambda e: e.group_points(ori, idx), grp(3, n, m1)),
+        ("group_c128_m128", lambda e: e.group_points(feats, idx2), grp(128, m1, m2)),
+        ("group_grad_c128_m128", lambda e: e.group_points_grad(go, idx2, 512), grp(128, m1, m2)),
+        ("group_grad_c3_m512", lambda e: e.group_points_grad(go3, idx, 1024), grp(3, n, m1)),
+    ]
+    ext = None
+    try:
+        from oracle import build_ref  # baseline leg: the reference's own kernels, never on the product path
+
+        ext = build_ref.load_ref()
+    except Exception:
+        ext = None
+    rec = {}
+    for name, fn, byts in cases:
+        us = time_events(lambda: fn(ops), 10, 3)
+        r = {"us": round(us, 2), "algorithmic_bytes": byts, "hbm_frac": round(byts / (us * 1e-6) / 1e9 / pk["hbm_gbs"], 4)}
+        if ext is not None:
+            try:
+                r["reference_kernel_sm100_us"] = round(time_events(lambda: fn(ext), 5, 2), 2)
+                r["speedup_vs_reference_kernel"] = round(r["reference_kernel_sm100_us"] / us, 2)
+            except Exception as e:  # noqa
+                r["reference_kernel_error"] = str(e)[:80]
+        rec[name] = r
+    return rec
+
+
+def sweep_record(dev):
+    """config[3]: kNN + kappa kernels, B=64, N in {1024,4096,10000}, k in {16,32}, hinted like inside the attack."""
+    from geoa3_b200 import ops, synth
+
+    pk = peaks()
+    B, rows = 64, []
+    for n in (1024, 4096, 10000):
+        pc, nr, _ = synth.make_batch(16, n)
+        ori = torch.from_numpy(np.tile(pc, (4, 1, 1))).to(dev)
+        nrm = torch.from_numpy(np.tile(nr, (4, 1, 1))).to(dev)
+        adv = ori + torch.from_numpy(synth.make_offsets(B, n)).to(dev)
+        prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
+        _, js, _, _ = ops.nn_pair(adv, ori)
+        pm, ipm = ops.visit_order(ori)
+        for k in (16, 32):
+            hn = ops.knn(prev, prev, k + 1, drop=1)[0]
+            t_plain = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1), 3, 1)
+            t_hint = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), 3, 1)
+            t_prune = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm), 3, 1)
+            nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
+            t_kap = time_events(lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr), 3, 1)
+            best = min(t_hint, t_prune)
+            byts = (28 + 4 * k) * B * n
+            rows.append({"n": n, "k": k, "knn_us": round(t_plain, 1), "knn_hinted_us": round(t_hint, 1),
+                         "knn_hinted_pruned_us": round(t_prune, 1), "kappa_us": round(t_kap, 1),
+                         "hbm_frac": round(byts / ((best + t_kap) * 1e-6) / 1e9 / pk["hbm_gbs"], 5),
+                         "fp32_tflops": round(8.0 * B * n * n / (best * 1e-6) / 1e12, 2)})
+    return rows
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+class CpuBatch(object):
+    """The oracle port of the attack step on the host cores, the 250-instance batch walked in chunks of 25 (a dense
+    [b,n,n] formulation of all 250 instances at once would need tens of GB; the reference's own CLI default is
+    batch_size 2, main_attack.py:326).  One step() = one real attack iteration of ALL instances."""
+
+    def __init__(self, b, with_net=True):
+        from geoa3_b200.victims import PointNet
+        from oracle import torch_port
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        net = PointNet(40).eval()
+        for p in net.parameters():
+            p.requires_grad_(False)
+        pc, nr, lab = make_inputs(b, NPTS, 0)
+        self.with_net = with_net
+        self.chunks = [torch_port.CpuAttackStep(net, torch.from_numpy(pc[i:i + CPU_CHUNK]), torch.from_numpy(nr[i:i + CPU_CHUNK]),
+                                                torch.from_numpy(lab[i:i + CPU_CHUNK]), KNN)
+                       for i in range(0, b, CPU_CHUNK)]
+
+    def step(self, only_first=False):
+        for c in (self.chunks[:1] if only_first else self.chunks):
+            c.step(self.with_net)
+
+
+def cpu_baseline_record(b):
+    """Bounded sample on the host cores: ONE real step of all `b` instances (after a one-chunk warm-up), plus
+    BASELINE config[0]: b=1, 10 iterations, loss-only and with PointNet."""
     from geoa3_b200.victims import PointNet
     from oracle import torch_port
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    job = CpuBatch(b)
+    job.step(only_first=True)
+    t0 = time.perf_counter()
+    job.step()
+    s_step = time.perf_counter() - t0
     torch.manual_seed(0)
     net = PointNet(40).eval()
-    pc, nr, lab = make_inputs(CPU_SAMPLE_B, NPTS, 0)
-    med, _ = torch_port.time_cpu_attack(net, torch.from_numpy(pc), torch.from_numpy(nr), torch.from_numpy(lab),
-                                        steps=steps, warmup=warmup, k=KNN)
-    per_instance_iter = med / CPU_SAMPLE_B
-    value = 1.0 / (per_instance_iter * B_PER_GPU)
-    return {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d instances x %d timed iterations (median), PointNet + CD/HD/curvature + backward + Adam, dense "
-                      "torch kNN as documented in the reference's comments; scaled to B=%d by instance count"
-                      % (CPU_SAMPLE_B, steps, B_PER_GPU),
-            "s_per_instance_iter": per_instance_iter}, med
+    pc, nr, lab = make_inputs(1, NPTS, 0)
+    args1 = (net, torch.from_numpy(pc), torch.from_numpy(nr), torch.from_numpy(lab))
+    med_full, _ = torch_port.time_cpu_attack(*args1, steps=10, warmup=2, k=KNN, with_net=True)
+    med_loss, _ = torch_port.time_cpu_attack(*args1, steps=10, warmup=2, k=KNN, with_net=False)
+    return {"value": 1.0 / s_step, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "cpu_model": cpu_model(),
+            "sample": "1 timed attack iteration of all %d instances (chunks of %d; PointNet + CD/HD/curvature + backward + "
+                      "Adam, dense torch kNN as documented in the reference's comments) after a one-chunk warm-up"
+                      % (b, CPU_CHUNK),
+            "s_per_step": round(s_step, 3),
+            "config0_b1_10iters": {"loss_only_fwd_bwd_adam_ms": round(med_loss * 1e3, 2),
+                                   "with_pointnet_ms": round(med_full * 1e3, 2), "stat": "median of 10"}}
 
 
 def run_reference(args):
+    """--impl reference: the CPU port for real at the headline config (all 250 instances per step), reduced step
+    count so the run ends within a few minutes; steps / warmup / ms_per_step are reported AS RUN."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.time()
-    cb, med = cpu_baseline(args.steps, max(args.warmup, 1), args.arch)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3 * B_PER_GPU / CPU_SAMPLE_B,
+    steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    job = CpuBatch(args.batch)
+    for _ in range(warm):
+        job.step()
+    ts = []
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        job.step()
+        ts.append(time.perf_counter() - t1)
+    total = sum(ts)
+    value = steps / total
+    cb = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "cpu_model": cpu_model(),
+          "sample": "%d timed + %d warm-up attack iterations of all %d instances (chunks of %d), nothing extrapolated"
+                    % (steps, warm, args.batch, CPU_CHUNK)}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "requested": {"steps": args.steps, "warmup": args.warmup},
+            "extrapolated": False, "ms_per_step": total / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1), "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": round(time.time() - t0, 2)}
     print(json.dumps(line))
 
@@ -220,64 +466,123 @@ def workload_config(args, world):
             "cuda_graph": not args.no_graph}
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+# ------------------------------------------------------------------ strong-scaling records
+def strong_record(args, rank, world, dev, gdist):
+    """config[1] as the north star states it: ONE `args.batch`-instance PointNet batch sharded over the ranks,
+    K steps + pack_stats + the final all-gather inside the timed region."""
+    total = args.batch
+    rows = gdist.shard_rows(total, world, rank)
+    st, pins = build_state("PointNet", len(rows), NPTS, rows.start, total, dev, rows=rows)
+    off_dev = pins[2].to(dev)
+    count_and_capture(st, off_dev, graph=not args.no_graph)
 
-    from geoa3_b200 import attack as atk
-    from geoa3_b200 import dist as gdist
-    from geoa3_b200 import ops
-    from geoa3_b200.victims import build_victim
+    def tail():
+        return gdist.gather_stats(gdist.state_stats(st), total)
 
-    rank, local_rank, world = gdist.init()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the GeoA3 hot path has no CPU fallback")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    b, n = args.batch, NPTS
-
-    torch.manual_seed(0)
-    net = build_victim(args.arch).to(dev).eval()
-    for p in net.parameters():
-        p.requires_grad_(False)
-    pc_h, nr_h, lab_h = make_inputs(b, n, rank * b)
-    pc_pin = torch.from_numpy(pc_h).pin_memory()
-    nr_pin = torch.from_numpy(nr_h).pin_memory()
-    off_pin = atk.default_offsets(b * world, n, 0, 0, gdist.shard_rows(b * world, world, rank)).pin_memory()
-    pc_ori, nrm = pc_pin.to(dev), nr_pin.to(dev)
-    target = torch.from_numpy(lab_h).to(dev)
-    cfg = atk.make_cfg(attack_label="Untarget", curv_loss_knn=KNN)
-    st = atk.AttackState(net, pc_ori, nrm, target, target, cfg, targeted=False, global_batch=b * world)
-    st.begin_search_step(0, off_pin.to(dev))
-
-    # count own kernel launches of one steady-state step (eager; the first step also pays the one-time arrangement
-    # of the original cloud), then capture
-    st.step()
-    ops.LAUNCHES = 0
-    st.step()
-    launches_per_step = ops.LAUNCHES
-    if not args.no_graph:
-        st.capture()
-    st.reset_global()
-    st.begin_search_step(0, off_pin.to(dev))
-
-    # ---------------- device-resident timing: W warm-up + K timed steps
-    for _ in range(args.warmup):
-        st.run_step()
-    sampler = ClockSampler(local_rank)
+    tail()  # warm the collective (NCCL communicator set-up is not part of an attack's steady state)
+    ms, stats = timed_steps(st, args.steps, args.warmup, dev, gdist, tail)
+    # the all-gather alone
     torch.cuda.synchronize()
     gdist.barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     e0.record()
-    for _ in range(args.steps):
-        st.run_step()
+    tail()
+    e1.record()
+    torch.cuda.synchronize()
+    ag_ms = gdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    rec = {"workload": "ONE %d-instance PointNet attack batch sharded by instance over %d rank(s): %d steps per rank + "
+                       "final all-gather of the [%d,%d] per-instance statistics (NCCL), device time max over ranks"
+                       % (total, world, args.steps, total, len(gdist.STAT_FIELDS)),
+           "scaling": "strong", "global_batch": total, "rows_per_rank": [len(gdist.shard_rows(total, world, r)) for r in range(world)],
+           "steps": args.steps, "ms_total": ms, "ms_per_step": ms / args.steps, "value": args.steps / (ms * 1e-3),
+           "unit": "attack-iters/s of the %d-instance batch" % total, "allgather_ms": ag_ms,
+           "stats_rows_gathered": int(stats.shape[0])}
+    del st
+    torch.cuda.empty_cache()
+    return rec
+
+
+def msg_record(args, rank, world, dev, gdist):
+    """config[4]: PointNet++ MSG attack on `--msg-total` instances sharded over the ranks; every rank walks its
+    rows in micro-batches of <= 250 through ONE captured step (AttackState.load_batch), then the all-gather."""
+    from geoa3_b200 import ops
+
+    total = args.msg_total
+    rows = gdist.shard_rows(total, world, rank)
+    micro = min(MSG_MICRO, len(rows))
+    nmb = (len(rows) + micro - 1) // micro
+    steps = max(1, min(args.steps, 3))
+    st, pins = build_state("PointNetPP_msg", micro, NPTS, rows.start, total, dev, rows=range(rows.start, rows.start + micro))
+    off_dev = pins[2].to(dev)
+    launches = count_and_capture(st, off_dev, graph=not args.no_graph)
+    batches = []
+    for i in range(nmb):  # device-resident inputs of every micro-batch (the last one is padded by wrapping around)
+        r0 = rows.start + min(i * micro, len(rows) - micro)
+        pc_h, nr_h, lab_h = make_inputs(micro, NPTS, r0)
+        batches.append((torch.from_numpy(pc_h).to(dev), torch.from_numpy(nr_h).to(dev), torch.from_numpy(lab_h).to(dev)))
+    blocks = []
+
+    def job():
+        del blocks[:]
+        for pc_d, nr_d, lab_d in batches:
+            st.load_batch(pc_d, nr_d, lab_d)
+            st.begin_search_step(0, off_dev)
+            for _ in range(steps):
+                st.run_step()
+            blocks.append(gdist.state_stats(st))
+        local = torch.cat(blocks, 0)[: len(rows)]
+        return gdist.gather_stats(local, total)
+
+    job()  # warm-up pass (also warms the collective)
+    torch.cuda.synchronize()
+    gdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stats = job()
     e1.record()
     torch.cuda.synchronize()
     gdist.barrier()
-    ms_total = gdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms = gdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    rec = {"workload": "PointNet++ MSG N=%d, %d instances sharded over %d rank(s), micro-batches of %d per rank through one "
+                       "captured step, %d attack iterations per instance + final all-gather (BASELINE config[4])"
+                       % (NPTS, total, world, micro, steps),
+           "scaling": "strong", "global_instances": total, "micro_batches_per_rank": nmb, "steps_per_instance": steps,
+           "ms_total": ms, "ms_per_microbatch_step": ms / (nmb * steps),
+           "value": total * steps / (ms * 1e-3), "unit": "instance-iterations/s (whole job, all GPUs)",
+           "own_launches_per_step": launches, "stats_rows_gathered": int(stats.shape[0])}
+    del st, batches
+    torch.cuda.empty_cache()
+    return rec
+
+
+def ssg_step_record(args, dev, gdist):
+    """config[2]: PointNet++ SSG attack step at B=250 (own FPS / ball_query / group_points every step)."""
+    st, pins = build_state("PointNetPP_ssg", args.batch, NPTS, 0, args.batch, dev)
+    launches = count_and_capture(st, pins[2].to(dev), graph=not args.no_graph)
+    steps = max(3, min(args.steps, 10))
+    ms, _ = timed_steps(st, steps, 2, dev, gdist)
+    del st
+    torch.cuda.empty_cache()
+    return {"workload": "PointNet++ SSG N=%d attack iteration, B=%d (BASELINE config[2])" % (NPTS, args.batch),
+            "ms_per_step": ms / steps, "value": steps / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "own_launches_per_step": launches}
+
+
+def headline(args, rank, local_rank, world, dev, gdist):
+    """The unchanged headline: device-resident steps (value) and the host-buffer e2e loop of config[1]."""
+    from geoa3_b200 import loss_utils
+
+    b, n = args.batch, NPTS
+    st, (pc_pin, nr_pin, off_pin) = build_state(args.arch, b, n, rank * b, b * world, dev)
+    pc_ori, nrm = st.pc_ori, st.normal_ori
+    launches_per_step = count_and_capture(st, off_pin.to(dev), graph=not args.no_graph)
+
+    # ---------------- device-resident timing: W warm-up + K timed steps
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        st.run_step()
+    sampler.start()
+    ms_total, _ = timed_steps(st, args.steps, 0, dev, gdist)
     clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
@@ -285,8 +590,6 @@ def main():
 
     # ---------------- end-to-end: host buffers in, loss out, every step
     loss_host = torch.empty(b, dtype=torch.float32).pin_memory()
-    from geoa3_b200 import loss_utils
-
     # Double-buffered input path: every step's inputs come from pinned host memory (H2D inside the timed region,
     # one set per step), but the copy for step i+1 runs on a copy stream WHILE step i computes; the step itself
     # only does a device-to-device move out of the staging buffers.
@@ -316,13 +619,11 @@ def main():
 
     consumed.record(torch.cuda.current_stream())
     prefetch()
-
     for _ in range(min(3, args.warmup)):
         e2e_step()
     st.step_idx.zero_()
     torch.cuda.synchronize()
     gdist.barrier()
-    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     e2e_steps = max(5, min(args.steps, 50))
@@ -345,22 +646,56 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "instance_iters_per_s": value * b, "final_loss": final_loss}
 
+    adv = (pc_ori + st.offset).detach().contiguous()
+    return line, adv, pc_ori.clone(), nrm.clone()
+
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from geoa3_b200 import dist as gdist
+    from geoa3_b200 import loss_utils
+
+    rank, local_rank, world = gdist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the GeoA3 hot path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    b, n = args.batch, NPTS
+
+    line, adv, pc_keep, nrm_keep = headline(args, rank, local_rank, world, dev, gdist)
+    loss_utils.clear_cache()
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    def guarded(name, fn):
+        try:
+            line[name] = fn()
+        except Exception as e:  # a failing sub-record must not cost the headline
+            line[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+    # ---------------- strong scaling (every N): config[1] sharded + final all-gather; config[4] MSG 2000 instances
+    guarded("strong", lambda: strong_record(args, rank, world, dev, gdist))
+    if not args.no_extras:
+        guarded("strong_msg", lambda: msg_record(args, rank, world, dev, gdist))
+
     if rank == 0:
         # ---------------- roofline of the dominant own kernel, measured live (CUDA events, current stream)
-        adv = (pc_ori + st.offset).detach().contiguous()
-        kb = kernel_breakdown(pc_ori, nrm, adv, KNN)
+        kb = kernel_breakdown(pc_keep, nrm_keep, adv, KNN)
         pk = peaks()
         top = max(kb, key=kb.get)
-        alg_bytes = {"nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n, "kappa_loss_fwd": (36 + 4 * KNN) * b * n,
-                     "loss_bwd": (56 + 4 * KNN) * b * n}[top]
-        alg_flop = {"nn_pair": 16.0 * b * n * n, "knn": 8.0 * b * n * n}.get(top, 0.0)
-        # DRAM bytes per launch of each kernel from the committed `ncu --set full` captures (profiles/ncu_r1_summary.md:
-        # dram__bytes_read.sum + dram__bytes_write.sum at this exact shape); outputs mostly stay in the 126 MB L2
-        ncu_traffic = {"knn": 19.48e6, "nn_pair": 8.20e6, "kappa_loss_fwd": 26.66e6, "loss_bwd": 29.76e6}
+        alg_bytes = {"arrange": 28 * b * n, "nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n,
+                     "knn_kappa": (12 + 4 * KNN + 24) * b * n, "kappa_loss_fwd": (36 + 4 * KNN) * b * n,
+                     "loss_reduce": 20 * b * n, "loss_bwd": (56 + 4 * KNN) * b * n}.get(top, 52 * b * n)
+        alg_flop = {"nn_pair": 16.0 * b * n * n, "knn": 8.0 * b * n * n, "knn_kappa": 8.0 * b * n * n}.get(top, 0.0)
         t_s = kb[top] * 1e-6
         achieved = alg_bytes / t_s / 1e9
         line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic.get(top), "peak_source": pk["source"],
+                            "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic().get(top), "peak_source": pk["source"],
                             "algorithmic_bytes_per_launch": alg_bytes,
                             "note": "distance kernels are FP32-issue bound (SURVEY §8d); see fp32",
                             "fp32": {"achieved_tflops": alg_flop / t_s / 1e12, "peak_tflops": pk["fp32_tflops"],
@@ -368,8 +703,24 @@ def main():
                                      "peak_source": "ubench/fp32_peak.cu measured on this pool"}}
         line["loss_fwd_bwd_us"] = dict(kb, total=round(sum(kb.values()), 2),
                                        hbm_frac_of_52BN=round(52 * b * n / (sum(kb.values()) * 1e-6) / 1e9 / pk["hbm_gbs"], 5))
+        if world == 1 and not args.no_extras:
+            guarded("gpu_reference_loss_us", lambda: {
+                "dense_torch_loss_fwd_bwd_us": dense_torch_loss_us(pc_keep, nrm_keep, adv, KNN),
+                "what": "CD + 0.1*HD + curvature(k=16) forward+backward at B=%d, N=%d with the dense [b,n,n] + topk "
+                        "formulation of Lib/loss_utils.py:30-31,54-56,67-69 in plain torch on this B200" % (b, n)})
+            torch.cuda.empty_cache()
+            cfgs = {}
+            line["configs"] = cfgs
+            for name, fn in (("2_pointnetpp_ssg_step", lambda: ssg_step_record(args, dev, gdist)),
+                             ("2_pointnetpp_ssg_ops", lambda: ssg_ops_record(b, dev)),
+                             ("3_curvature_sweep_B64", lambda: sweep_record(dev))):
+                try:
+                    cfgs[name] = fn()
+                except Exception as e:
+                    cfgs[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline(5, 1, args.arch)
+            guarded("cpu_baseline", lambda: cpu_baseline_record(b))
         print(json.dumps(line))
     gdist.barrier()
     if torch.distributed.is_initialized():

@@ -189,6 +189,22 @@ class AttackState(object):
             self.last_pred.zero_()
             self.loss_log.zero_()
 
+    def load_batch(self, pc_ori, normal_ori, target, gt_target=None):
+        """Next batch of the SAME shape into the existing device buffers (in place, so a captured CUDA graph stays
+        valid): the loop `for batch in loader: attack(batch)` of main_attack.py:174-227 then captures its step once
+        instead of once per batch.  Everything derived from the originals is refreshed in place too."""
+        with torch.no_grad():
+            self.pc_ori.copy_(pc_ori)
+            self.normal_ori.copy_(normal_ori)
+            self.target.copy_(target)
+            if self.gt_target is not self.target:
+                self.gt_target.copy_(gt_target if gt_target is not None else target)
+            if self.kappa_ori is not None:
+                self.kappa_ori.copy_(loss_utils._get_kappa_ori(self.pc_ori, self.normal_ori,
+                                                               _get(self.cfg, "curv_loss_knn")).detach())
+            self.hints.refresh_order(self.pc_ori)
+        self.reset_global()
+
     # -- per binary-search-step reset (:231-236, :264-277)
     def begin_search_step(self, search_step, init_offset):
         with torch.no_grad():
@@ -262,7 +278,7 @@ class AttackState(object):
         with torch.no_grad():
             if _get(cfg, "is_pro_grad"):
                 if _get(cfg, "is_real_offset"):
-                    self.offset.copy_(find_offset(self.pc_ori, self.pc_ori + self.offset))
+                    self.offset.copy_(find_offset(self.pc_ori, self.base + self.offset))  # periodical_pc + offset (:345)
                 self.offset.copy_(offset_proj(self.offset, self.pc_ori, self.normal_ori))
             if _get(cfg, "cc_linf") != 0:
                 self.offset.copy_(lp_clip(self.offset, _get(cfg, "cc_linf")))
@@ -359,31 +375,55 @@ def default_offsets(global_batch, n, search_step, seed=0, rows=None):
     return full if rows is None else full[rows]
 
 
+class frozen_parameters(object):
+    """Context manager: the victim's parameters do not require grad inside (restored on exit).  The attack only
+    differentiates w.r.t. the perturbation; with trainable parameters autograd would also run every layer's
+    weight-gradient kernels each step (the reference pays for them: its nets keep requires_grad=True)."""
+
+    def __init__(self, net):
+        self.params = [p for p in net.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+        return self
+
+    def __exit__(self, *exc):
+        for p in self.params:
+            p.requires_grad_(True)
+        return False
+
+
 def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=False, use_cuda_graph=True,
-           global_batch=None, rows=None, seed=0, device=None):
+           global_batch=None, rows=None, seed=0, device=None, return_state=False):
     """Drop-in for geoA3_attack.attack(net, input_data, cfg, i, loader_len, saved_dir).
 
     Extra keyword arguments (all optional): `global_batch` / `rows` describe the shard of a larger batch
-    this process owns (loss scaling + initial offsets), `use_cuda_graph` replays the captured step."""
+    this process owns (loss scaling + initial offsets), `use_cuda_graph` replays the captured step,
+    `ref_quirks=True` reproduces the reference's stale-`output_label` coupling in the scale-const update (:375;
+    the default implements the evident per-instance intent — see INTEGRATION.md section 4), `return_state=True`
+    appends the AttackState (device-side per-instance statistics for dist.attack_sharded).
+    The victim's parameters are frozen for the duration of the call (no weight-gradient kernels) and restored."""
     device = device or torch.device("cuda", torch.cuda.current_device())
     targeted = _get(cfg, "attack_label") != "Untarget"
     pc_ori, normal_ori, target, gt_target = _unpack(input_data, cfg, device)
     b, _, n = pc_ori.shape
     gb = global_batch if global_batch is not None else b
-    st = AttackState(net, pc_ori, normal_ori, target, gt_target, cfg, targeted, global_batch=gb)
     steps = _get(cfg, "iter_max_steps")
-    graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample and not st.partial and not st.jitter_on  # (host-side random picks / periods)
-    if graphable:
-        st.begin_search_step(0, default_offsets(gb, n, 0, seed, rows).to(device))
-        st.capture()
-        st.reset_global()  # the capture warm-up advanced the state; start over
-    for search_step in range(_get(cfg, "binary_max_steps")):
-        init = default_offsets(gb, n, search_step, seed, rows).to(device)
-        st.begin_search_step(search_step, init)
-        for _ in range(steps):
-            st.run_step()
-        st.end_search_step(ref_quirks=ref_quirks)
-    torch.cuda.synchronize(device)
+    with frozen_parameters(net):
+        st = AttackState(net, pc_ori, normal_ori, target, gt_target, cfg, targeted, global_batch=gb)
+        graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample and not st.partial and not st.jitter_on  # (host-side random picks / periods)
+        if graphable:
+            st.begin_search_step(0, default_offsets(gb, n, 0, seed, rows).to(device))
+            st.capture()
+            st.reset_global()  # the capture warm-up advanced the state; start over
+        for search_step in range(_get(cfg, "binary_max_steps")):
+            init = default_offsets(gb, n, search_step, seed, rows).to(device)
+            st.begin_search_step(search_step, init)
+            for _ in range(steps):
+                st.run_step()
+            st.end_search_step(ref_quirks=ref_quirks)
+        torch.cuda.synchronize(device)
     best_loss = st.best_loss.cpu().numpy()
-    return (st.best_attack, target, (best_loss < 1e10), st.best_attack_step.cpu().tolist(),
-            st.loss_log.cpu().tolist())
+    out = (st.best_attack, target, (best_loss < 1e10), st.best_attack_step.cpu().tolist(), st.loss_log.cpu().tolist())
+    return out + (st,) if return_state else out

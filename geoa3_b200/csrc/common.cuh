@@ -69,4 +69,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only, so "done once" has to be remembered per device
+// (a process may drive several GPUs).  One bit per device ordinal; the attribute is idempotent, so a benign
+// race at worst repeats the call.
+struct PerDeviceOnce {
+  unsigned long long mask = 0ull;
+  int dev = 0;
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return !((mask >> (dev & 63)) & 1ull);
+  }
+  void done() { mask |= 1ull << (dev & 63); }
+};
+
+
 }  // namespace geoa3

@@ -279,22 +279,19 @@ loss_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, co
 static bool plan_bwd_layout(int n, int m, int k, bool do_curv, bool do_col, BwdLayout* L) {
   const int budget = 227 * 1024 - 256;
   L->k_magic = k > 1 ? (unsigned)(((1ull << 32) + (unsigned)k - 1) / (unsigned)k) : 0u;
-  for (int W = 16; W >= 1; W >>= 1) {
-    int off = 0;
-    auto take = [&](size_t bytes) { int o = off; off += (int)((bytes + 15) & ~(size_t)15); return o; };
-    L->pts = take((size_t)16 * n);
-    L->nrm = take(do_curv ? (size_t)16 * n : 0);
-    L->offs1 = take(do_curv ? (size_t)4 * (n + 1) : 0);
-    L->offs2 = take(do_col ? (size_t)4 * (n + 1) : 0);
-    L->whist = take(do_curv ? (size_t)2 * W * ((n + 1) & ~1) : (do_col ? (size_t)4 * n : 0));
-    L->ent1 = take(do_curv ? (size_t)2 * n * k : 0);
-    L->ent2 = take(do_col ? (size_t)2 * m : 0);
-    L->total = off;
-    L->W = W;
-    // prefer two resident CTAs per SM while at least 4 builder warps remain
-    if (off <= budget / 2 || (W <= 4 && off <= budget)) return true;
-  }
-  return L->total <= budget;
+  int off = 0;
+  auto take = [&](size_t bytes) { int o = off; off += (int)((bytes + 15) & ~(size_t)15); return o; };
+  L->pts = take((size_t)16 * n);
+  L->nrm = take(do_curv ? (size_t)16 * n : 0);
+  L->offs1 = take(do_curv ? (size_t)4 * (n + 1) : 0);
+  L->offs2 = take(do_col ? (size_t)4 * (n + 1) : 0);
+  // build_csr_sorted() uses this as `int cnt[n]` (counters, then fill cursors) for BOTH lists, one after the other
+  L->whist = take((do_curv || do_col) ? (size_t)4 * n : 0);
+  L->ent1 = take(do_curv ? (size_t)2 * n * k : 0);
+  L->ent2 = take(do_col ? (size_t)2 * m : 0);
+  L->total = off;
+  L->W = 1;
+  return off <= budget;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -430,12 +427,12 @@ extern "C" int geoa3_kappa_loss_fwd(const float* pc, const float* normal, const 
   if (cd || hd || hd_arg) GEOA3_CHECK_ARG(d_a2o);
   const size_t smem = do_kappa ? (size_t)16 * n : 0;
   if (smem > 227 * 1024 - 1024) return GEOA3_EUNSUPPORTED;
-  static bool attr_done = false;  // idempotent attribute: a benign race at worst repeats the call
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kappa_loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024 - 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.done();
   }
   kappa_loss_fwd_kernel<<<b, KL_THREADS, smem, (cudaStream_t)stream>>>(
       pc, normal, m, jstar, nbr, k, d_a2o, d_o2a, m, kappa_ori, n, kappa, nrm_out, cd, hd, hd_arg, curv);
@@ -468,12 +465,12 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
   cudaStream_t s = (cudaStream_t)stream;
   BwdLayout L;
   if (bwd_fused_ok(n, m, k, do_curv, do_col, &L)) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.needed()) {
       cudaError_t e = cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024 - 256);
       if (e != cudaSuccess) return (int)e;
-      attr_done = true;
+      attr_done.done();
     }
     loss_bwd_kernel<<<b, BW_THREADS, L.total, s>>>(adv, ori, nrm_adv, kappa_adv, kappa_ori, jstar, istar, nbr, hd_arg,
                                                    g_cd, g_hd, g_cu, g_kappa, n, m, k, grad_adv, L);
@@ -487,11 +484,11 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
   while (W > 1 && (size_t)W * ((n + 1) & ~1) * 4 > 160 * 1024) W >>= 1;
   const size_t hsm = (size_t)W * ((n + 1) & ~1) * 4;
   if (hsm > 200 * 1024) return GEOA3_EUNSUPPORTED;
-  static bool attr_l = false;
-  if (!attr_l) {
+  static PerDeviceOnce attr_l;
+  if (attr_l.needed()) {
     cudaError_t e = cudaFuncSetAttribute(bwd_large_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_l = true;
+    attr_l.done();
   }
   int err;
   if (do_curv) {

@@ -927,25 +927,25 @@ static int run_csr_grad(const float* grad_out, const float* weight, const int32_
   const int W = pick_W(n, CSRG_THREADS);
   const size_t sm1 = (size_t)W * ((n + 1) & ~1) * 4;
   if (sm1 > 200 * 1024) return GEOA3_EUNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.needed()) {
     cudaError_t e = cudaFuncSetAttribute(csr_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(csr_gather_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.done();
   }
   csr_global_kernel<<<b, CSRG_THREADS, sm1, s>>>(idx, E, n, W, csr, fast_flag);
   int err = GEOA3_LAUNCH_RESULT();
   if (err) return err;
   const size_t coop_smem = (size_t)E * 4 + (size_t)((n + 1 + 3) & ~3) * 4 + (size_t)E * 2;
   if (!weight && e_div == 1 && c >= GG2_CC && (E & 3) == 0 && E <= 65536 && coop_smem <= 110 * 1024) {
-    static bool coop_attr = false;
-    if (!coop_attr) {
+    static PerDeviceOnce coop_attr;
+    if (coop_attr.needed()) {
       cudaError_t e = cudaFuncSetAttribute(csr_gather_grad_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            110 * 1024);
       if (e != cudaSuccess) return (int)e;
-      coop_attr = true;
+      coop_attr.done();
     }
     csr_gather_grad_coop_kernel<<<dim3(ceil_div(c, GG2_CC), b), GG2_THREADS, coop_smem, s>>>(
         grad_out, csr, c, n, E, grad_points, fast_flag);
@@ -1086,8 +1086,8 @@ static int run_fps(const float* xyz, int b, int n, int m, const int32_t* start, 
   int bits = 0;
   while ((1 << bits) < bs) ++bits;
   if (start) bits = 0;  // ties -> lowest index
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.needed()) {
     cudaError_t e = cudaSuccess;
 #define GEOA3_FPS_ATTR(P_, M_) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<P_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
@@ -1096,7 +1096,7 @@ static int run_fps(const float* xyz, int b, int n, int m, const int32_t* start, 
     GEOA3_FPS_ATTR(4, 2); GEOA3_FPS_ATTR(8, 2); GEOA3_FPS_ATTR(16, 2);
 #undef GEOA3_FPS_ATTR
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.done();
   }
   // norm arithmetic of the plain variant: separately rounded squares — what torch's CUDA norm reduction computes
   // (tools/time_kernels.py --fps-plain: picks identical to the torch loop; GEOA3_FPS_NORM=1 selects the fma chain,
@@ -1124,20 +1124,20 @@ extern "C" int geoa3_ball_query(const float* new_xyz, const float* xyz, int b, i
   if (nsample > BQ_MAX_NS || b > 65535) return GEOA3_EUNSUPPORTED;
   const size_t smem = (size_t)((n + 63) & ~63) * 12;
   if (smem > 200 * 1024) return GEOA3_EUNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.done();
   }
   if (n <= 65535 && !getenv("GEOA3_BQ_WARP")) {  // (env: A/B knob for tools/time_kernels.py, not part of the API)
     const size_t hs = (size_t)BQT_THREADS * (nsample + 2) * sizeof(uint16_t);
-    static bool attr_t = false;
-    if (!attr_t) {
+    static PerDeviceOnce attr_t;
+    if (attr_t.needed()) {
       cudaError_t e = cudaFuncSetAttribute(ball_query_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            BQT_THREADS * (BQ_MAX_NS + 2) * (int)sizeof(uint16_t));
       if (e != cudaSuccess) return (int)e;
-      attr_t = true;
+      attr_t.done();
     }
     ball_query_thread_kernel<<<dim3(ceil_div(m, BQT_THREADS), b), BQT_THREADS, hs, (cudaStream_t)stream>>>(
         new_xyz, xyz, n, m, radius, nsample, idx);
@@ -1156,11 +1156,11 @@ extern "C" int geoa3_group_points(const float* points, const int32_t* idx, int b
   // channels per CTA limited by shared memory (GP_CC rows of n floats)
   const size_t smem = (size_t)(c < GP_CC ? c : GP_CC) * n * 4;
   if (smem > 200 * 1024) return GEOA3_EUNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.needed()) {
     cudaError_t e = cudaFuncSetAttribute(group_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.done();
   }
   dim3 grid(ceil_div(E, GP_ETILE), ceil_div(c, GP_CC), b);
   group_points_kernel<<<grid, GP_THREADS, smem, (cudaStream_t)stream>>>(points, idx, c, n, E, out);

@@ -68,6 +68,16 @@ class HintBuffers(object):
             self.perm, self.iperm = ops.visit_order(ori)
             self.ori_arranged = ops.arrange(ori, self.perm)
 
+    def refresh_order(self, ori):
+        """The original cloud's CONTENTS changed (AttackState.load_batch): recompute the visiting order into the
+        existing tensors (their addresses are baked into a captured CUDA graph)."""
+        if self.perm is None or self.perm.shape != (ori.shape[0], ori.shape[2]):
+            return  # nothing computed yet; ensure_order() will do it on first use
+        perm, iperm = ops.visit_order(ori)
+        self.perm.copy_(perm)
+        self.iperm.copy_(iperm)
+        self.ori_arranged.copy_(ops.arrange(ori, self.perm))
+
     def ensure_nn(self, b, n, m, dev):
         if self.jstar is None or self.jstar.shape != (b, n) or self.istar.shape != (b, m):
             self.d1 = torch.empty(b, n, device=dev, dtype=torch.float32)
@@ -106,6 +116,10 @@ class _Entry(object):
                 and self.ori_ver == ori._version)
 
 
+# Cache contract: a hit needs the SAME tensor objects with unchanged `_version` counters.  In-place ops bump the
+# version; swapping storage behind torch's back (`adv.data = other`, the reference's idiom at
+# Attacker/geoA3_attack.py:345-352) does NOT — call clear_cache() after such a swap.  The caches are per process and
+# not synchronised: use one attack per process / thread (the deployment model is one process per GPU).
 _CACHE = []
 _CACHE_MAX = 4
 
@@ -153,16 +167,7 @@ def _nn(e, both):
         if hb is NO_HINTS:
             e.d1, e.jstar, e.d2, e.istar = ops.nn_pair(e.adv_c, e.ori_c, both=True)
         elif hb is not None:  # persistent buffers: hint and result alias, refreshed in place
-            hb.ensure_nn(b, n, m, e.adv_c.device)
-            if n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
-                hb.ensure_order(e.ori_c)
-                ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, perm_a=hb.perm, perm_o=hb.perm,
-                            iperm_a=hb.iperm, iperm_o=hb.iperm, ori_arranged=hb.ori_arranged,
-                            out=(hb.d1, hb.jstar, hb.d2, hb.istar))
-            else:
-                ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar,
-                            out=(hb.d1, hb.jstar, hb.d2, hb.istar))
-            e.d1, e.jstar, e.d2, e.istar = hb.d1, hb.jstar, hb.d2, hb.istar
+            _launch_nn_hinted(e, hb)
         else:
             key = (e.adv_c.device, b, n, m)
             prev = _LAST.get(key)
@@ -178,13 +183,15 @@ def _nn(e, both):
     return e
 
 
-def _reductions(e):
+def _reductions(e, one_sided=False):
+    """CD / HD(+argmax) of the cached 1-NN distances; the one-sided mean (pseudo_chamfer_loss) only on demand."""
     if e.red is None:
         _nn(e, True)
         e.red = ops.kappa_loss_fwd(e.adv_c, d_a2o=e.d1, d_o2a=e.d2, m=e.ori_c.shape[2], want_kappa=False,
                                    want_cd=True, want_hd=True)
-        one = ops.kappa_loss_fwd(e.adv_c, d_a2o=e.d1, d_o2a=None, m=e.ori_c.shape[2], want_kappa=False, want_cd=True)
-        e.red["cd_one_sided"] = one["cd"]
+    if one_sided and "cd_one_sided" not in e.red:
+        e.red["cd_one_sided"] = ops.kappa_loss_fwd(e.adv_c, d_a2o=e.d1, d_o2a=None, m=e.ori_c.shape[2],
+                                                   want_kappa=False, want_cd=True)["cd"]
     return e.red
 
 
@@ -197,18 +204,83 @@ def _nbr(e, k):
             buf = hb.nbr.get(k)
             if buf is None or buf.shape[:2] != e.adv_c.shape[::2]:
                 hb.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1)[0]  # first call: nothing to hint with
-            elif (hb.perm is not None and k <= 16 and e.adv_c.shape[2] >= hb.prune_min_n_knn
-                  and e.adv_c.shape[2] == hb.perm.shape[1]):  # measured: pays for n >= 2048 and K <= 17 only
-                ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, perm_q=hb.perm, perm_c=hb.perm,
-                        iperm_c=hb.iperm)
             else:
-                ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf)
+                _launch_knn_hinted(e, k, hb)
             e.nbr[k] = hb.nbr[k]
         else:
             key = (e.adv_c.device,) + tuple(e.adv_c.shape) + (k,)
             e.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=_LAST.get(key))[0]
             _LAST[key] = e.nbr[k]
     return e.nbr[k]
+
+
+# ---------------------------------------------------------------------------- the launches of one attack step
+# Each own kernel of the steady-state step is issued from exactly one function, used both by the autograd nodes
+# below and by `step_plan` (bench.py / tools time these closures, so what is timed is what the attack runs).
+def _launch_nn_hinted(e, hb):
+    b, _, n = e.adv_c.shape
+    m = e.ori_c.shape[2]
+    hb.ensure_nn(b, n, m, e.adv_c.device)
+    if n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
+        hb.ensure_order(e.ori_c)
+        ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, perm_a=hb.perm, perm_o=hb.perm,
+                    iperm_a=hb.iperm, iperm_o=hb.iperm, ori_arranged=hb.ori_arranged,
+                    out=(hb.d1, hb.jstar, hb.d2, hb.istar))
+    else:
+        ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, out=(hb.d1, hb.jstar, hb.d2, hb.istar))
+    e.d1, e.jstar, e.d2, e.istar = hb.d1, hb.jstar, hb.d2, hb.istar
+
+
+def _launch_knn_hinted(e, k, hb):
+    buf = hb.nbr[k]
+    if (hb.perm is not None and k <= 16 and e.adv_c.shape[2] >= hb.prune_min_n_knn
+            and e.adv_c.shape[2] == hb.perm.shape[1]):  # measured: pays for n >= 2048 and K <= 17 only
+        ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, perm_q=hb.perm, perm_c=hb.perm, iperm_c=hb.iperm)
+    else:
+        ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf)
+
+
+def _launch_geo_fwd(e, nrm_src, kappa_ori, nbr, single_side, use_curv):
+    return ops.kappa_loss_fwd(
+        e.adv_c, normal=nrm_src if use_curv else None, jstar=e.jstar, nbr=nbr, d_a2o=e.d1,
+        d_o2a=None if single_side else e.d2, kappa_ori=kappa_ori if use_curv else None, m=e.ori_c.shape[2],
+        want_kappa=use_curv, want_nrm=use_curv, want_cd=True, want_hd=True, want_curv=use_curv)
+
+
+def _launch_geo_bwd(e, out, nbr, kappa_ori, g_cd, g_hd, g_cu, single_side):
+    return ops.loss_bwd(e.adv_c, ori=e.ori_c, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=kappa_ori,
+                        jstar=e.jstar, istar=None if single_side else e.istar, nbr=nbr, hd_arg=out["hd_arg"],
+                        g_cd=g_cd, g_hd=g_hd, g_cu=g_cu)
+
+
+def step_plan(adv, ori, ori_normal, ori_kappa, k, hints, w=(1.0, 0.1, 1.0)):
+    """Runs the fused loss forward of one attack step on `adv` through the persistent `hints` (exactly what
+    `geo_loss(..., hints=hints)` launches) and returns {"out": forward results, "launches": f} where f(g) lists
+    (name, closure) for every own kernel of the step's forward AND backward with upstream gradient g [b] —
+    measurement hooks for bench.py and tools/; results are identical to the autograd path."""
+    e = _Entry()
+    e.hints = hints
+    e.adv_ref = e.ori_ref = lambda: None
+    e.adv_ver = e.ori_ver = -1
+    e.adv_c, e.ori_c = _as_input(adv, "adv_pc"), _as_input(ori, "ori_pc")
+    e.d1 = e.jstar = e.d2 = e.istar = e.red = None
+    e.nbr, e.kap = {}, {}
+    nrm_src = _as_input(ori_normal, "ori_normal")
+    ko = ori_kappa.detach().float().contiguous()
+    _launch_nn_hinted(e, hints)
+    nbr = _nbr(e, k)
+    out = _launch_geo_fwd(e, nrm_src, ko, nbr, False, True)
+
+    def launches(g):
+        g = g.detach().float().contiguous()
+        gs = [(g * w_) .contiguous() for w_ in w]
+        return [("nn_pair", lambda: _launch_nn_hinted(e, hints)),
+                ("knn", lambda: _launch_knn_hinted(e, k, hints)),
+                ("kappa_loss_fwd", lambda: _launch_geo_fwd(e, nrm_src, ko, nbr, False, True)),
+                ("loss_bwd", lambda: _launch_geo_bwd(e, out, nbr, ko, gs[0], gs[1], gs[2], False))]
+
+    return {"out": out, "entry": e, "nbr": nbr, "launches": launches}
+
 
 
 def _grad_vec(g, like):
@@ -220,7 +292,7 @@ class _Chamfer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adv_pc, ori_pc, both):
         e = _nn(_entry(adv_pc, ori_pc), True)
-        red = _reductions(e)
+        red = _reductions(e, one_sided=not both)
         ctx.e, ctx.both = e, both
         return (red["cd"] if both else red["cd_one_sided"]).clone()
 
@@ -289,17 +361,14 @@ class _GeoLoss(torch.autograd.Function):
         e = _nn(_entry(adv_pc, ori_pc, hints), True)
         use_curv = w_curv != 0 and k > 0
         nbr = _nbr(e, k) if use_curv else None
-        out = ops.kappa_loss_fwd(
-            e.adv_c, normal=_as_input(ori_normal, "ori_normal") if use_curv else None, jstar=e.jstar, nbr=nbr,
-            d_a2o=e.d1, d_o2a=None if single_side else e.d2,
-            kappa_ori=ori_kappa.detach().float().contiguous() if use_curv else None, m=e.ori_c.shape[2],
-            want_kappa=use_curv, want_nrm=use_curv, want_cd=True, want_hd=True, want_curv=use_curv)
+        ko = ori_kappa.detach().float().contiguous() if use_curv else None
+        out = _launch_geo_fwd(e, _as_input(ori_normal, "ori_normal") if use_curv else None, ko, nbr, single_side, use_curv)
         cd, hd = out["cd"], out["hd"]
         curv = out["curv"] if use_curv else torch.zeros_like(cd)
         total = w_cd * cd + w_hd * hd + (w_curv * curv if use_curv else 0.0)
         ctx.e, ctx.out, ctx.nbr = e, out, nbr
         ctx.w = (w_cd, w_hd, w_curv, single_side, use_curv)
-        ctx.kappa_ori = ori_kappa.detach().float().contiguous() if use_curv else None
+        ctx.kappa_ori = ko
         ctx.mark_non_differentiable(cd, hd, curv)
         return total, cd, hd, curv
 
@@ -308,11 +377,8 @@ class _GeoLoss(torch.autograd.Function):
         e, out = ctx.e, ctx.out
         w_cd, w_hd, w_curv, single_side, use_curv = ctx.w
         g = _grad_vec(g, e.adv_c)
-        grad = ops.loss_bwd(
-            e.adv_c, ori=e.ori_c, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=ctx.kappa_ori, jstar=e.jstar,
-            istar=None if single_side else e.istar, nbr=ctx.nbr, hd_arg=out["hd_arg"],
-            g_cd=(g * w_cd) if w_cd != 0 else None, g_hd=(g * w_hd) if w_hd != 0 else None,
-            g_cu=(g * w_curv) if use_curv else None)
+        grad = _launch_geo_bwd(e, out, ctx.nbr, ctx.kappa_ori, (g * w_cd) if w_cd != 0 else None,
+                               (g * w_hd) if w_hd != 0 else None, (g * w_curv) if use_curv else None, single_side)
         return (grad,) + (None,) * 9
 
 

@@ -13,8 +13,14 @@
  *   - loss-side clouds are channel-first float32 [b][3][n] (what Lib/loss_utils.py receives);
  *     pointnet2-side coordinates are AoS float32 [b][n][3] and features [b][c][n]
  *     (the pointnet2_ops convention); every index tensor is int32.
- *   - index outputs are bit-exact w.r.t. the pinned arithmetic d = fma(dz,dz,fma(dy,dy,dx*dx)),
- *     ties -> lowest index; reductions are fixed-order (run-to-run deterministic, no float atomics).
+ *   - index outputs are bit-exact w.r.t. TWO pinned squared-distance chains:
+ *       loss side (geoa3_nn_pair, geoa3_knn):  t = dx*dx; t = fma(dy,dy,t); t = fma(dz,dz,t)
+ *         (pytorch3d's `dist += diff*diff` loop under nvcc's default -fmad=true);
+ *       pointnet2 side (FPS, ball_query, three_nn):  t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)
+ *         (what nvcc makes of the reference's (dx*dx)+(dy*dy)+(dz*dz): read off the SASS of the
+ *         reference sources built for sm_100, and checked against that binary);
+ *     ties -> lowest index (FPS: the reference's tournament order); reductions are fixed-order
+ *     (run-to-run deterministic, no float atomics).
  *
  * Paths are relative to the reference checkout (Gorilla-Lab-SCUT/GeoA3).
  */

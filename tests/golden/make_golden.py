@@ -36,7 +36,7 @@ AUX_CASES = [
 ]
 
 
-def main(which=("loss", "aux", "defense", "fps", "normal")):
+def main(which=("loss", "l2", "aux", "defense", "fps", "normal")):
     torch.manual_seed(0)
     torch.set_num_threads(4)
     for name, b, n, k, std, start in (CASES if "loss" in which else []):
@@ -51,6 +51,19 @@ def main(which=("loss", "aux", "defense", "fps", "normal")):
             out["f64_" + key] = v
         np.savez_compressed(osp.join(HERE, name + ".npz"), **out)
         print(name, "cd", r32["cd"], "hd", r32["hd"], "curv", r32["curv"])
+
+    # norm_l2_loss (Lib/loss_utils.py:25-26): value and autograd gradient of the reference function, fp32 + fp64
+    if "l2" in which:
+        pc, _, _ = synth.make_batch(3, 200, 2)
+        adv = pc + synth.make_offsets(3, 200, seed=5, std=3e-2)
+        out = dict(adv=adv, ori=pc)
+        for tag, dt in (("f32_", torch.float32), ("f64_", torch.float64)):
+            a = torch.from_numpy(adv).to(dt).requires_grad_(True)
+            v = ref_loader.load().norm_l2_loss(a, torch.from_numpy(pc).to(dt))
+            v.sum().backward()
+            out[tag + "l2"], out[tag + "grad"] = v.detach().numpy(), a.grad.numpy()
+        np.savez_compressed(osp.join(HERE, "l2_case.npz"), **out)
+        print("l2_case", out["f32_l2"])
 
     # neighbourhood regularisers (Lib/loss_utils.py:99-190), same reference module, k neighbours
     for name, b, n, k, std, start in (AUX_CASES if "aux" in which else []):
@@ -101,4 +114,4 @@ def main(which=("loss", "aux", "defense", "fps", "normal")):
 
 
 if __name__ == "__main__":
-    main(tuple(sys.argv[1:]) or ("loss", "aux", "defense", "fps", "normal"))   # e.g. `make_golden.py aux` regenerates only aux_*
+    main(tuple(sys.argv[1:]) or ("loss", "l2", "aux", "defense", "fps", "normal"))   # e.g. `make_golden.py aux` regenerates only aux_*
