@@ -19,6 +19,7 @@ SIGNATURES = {
     "geoa3_error_string": (C.c_char_p, [_i]),
     "geoa3_nn_pair": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 11),
     "geoa3_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "geoa3_knn_set": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "geoa3_group_bbox_floats": (_sz, [_i]),
     "geoa3_group_bbox": (_i, [_vp, _i, _i, _vp, _vp]),
     "geoa3_arrange": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -12,7 +12,7 @@ import sys
 HERE = osp.dirname(osp.abspath(__file__))
 CSRC = osp.join(HERE, "csrc")
 SO = osp.join(HERE, "libgeoa3_b200.so")
-SOURCES = ["nn_pair.cu", "knn.cu", "kappa_loss.cu", "pointnet2.cu"]
+SOURCES = ["nn_pair.cu", "knn.cu", "knn_select.cu", "kappa_loss.cu", "pointnet2.cu"]
 HEADERS = ["common.cuh", "csr.cuh", osp.join("..", "..", "include", "geoa3_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,13 +39,29 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Every source is compiled to an object in parallel (one nvcc per file), then linked into the .so."""
     if not force and not needs_build():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [osp.join(CSRC, s) for s in SOURCES] + ["-o", SO]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    objdir = osp.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    flags += os.environ.get("GEOA3_NVCC_DEFS", "").split()  # experiment knobs (-DNAME=value), never set in production
+    hdr_t = max(osp.getmtime(osp.join(CSRC, h)) for h in HEADERS if osp.exists(osp.join(CSRC, h)))
+    jobs, objs = [], []
+    for src in SOURCES:
+        obj = osp.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        srcp = osp.join(CSRC, src)
+        if not force and osp.exists(obj) and osp.getmtime(obj) > max(osp.getmtime(srcp), hdr_t, osp.getmtime(osp.abspath(__file__))):
+            continue
+        cmd = [_nvcc()] + flags + ["-c", srcp, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        jobs.append((src, subprocess.Popen(cmd)))
+    failed = [src for src, p in jobs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(failed))
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs)
     return SO
 
 

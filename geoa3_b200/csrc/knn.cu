@@ -316,6 +316,12 @@ __global__ void group_bbox_kernel(const float* __restrict__ pc, const int32_t* _
 
 }  // namespace geoa3
 
+namespace geoa3 {
+int launch_knn_select(const float* query, const float* ref, int b, int n, int m, int K, int kout, int drop,
+                      const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const float* bb_c,
+                      const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s);  // knn_select.cu
+}
+
 extern "C" size_t geoa3_group_bbox_floats(int n) {
   return (size_t)(((n + 31) >> 5) + (n + geoa3::KNN_CHUNK - 1) / geoa3::KNN_CHUNK) * 8;
 }
@@ -360,4 +366,20 @@ extern "C" int geoa3_knn(const float* query, const float* ref, int b, int n, int
   if (K <= 17) return launch_knn<17>(GEOA3_KNN_ARGS);
   return launch_knn<33>(GEOA3_KNN_ARGS);
 #undef GEOA3_KNN_ARGS
+}
+
+extern "C" int geoa3_knn_set(const float* query, const float* ref, int b, int n, int m, int K, int drop,
+                             const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const float* bb_c,
+                             const int32_t* hint, int hint_k, int32_t* idx, float* dist, geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(query && ref && idx);
+  GEOA3_CHECK_ARG((perm_c == nullptr) == (bb_c == nullptr));
+  GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
+  if (K > GEOA3_KNN_MAX_K || b > 65535) return GEOA3_EUNSUPPORTED;
+  if (K > m) return GEOA3_EINVAL;
+  const int r = launch_knn_select(query, ref, b, n, m, K, K - drop, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx,
+                                  dist, (cudaStream_t)stream);
+  if (r != INT_MIN) return r;
+  // clouds beyond 65 535 points: the sorted list of geoa3_knn is one valid order of the same members
+  return geoa3_knn(query, ref, b, n, m, K, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx, dist, stream);
 }

@@ -109,7 +109,7 @@ def _order_of(ori_obj, ori_c):
 # ---------------------------------------------------------------------------- per-step cache
 class _Entry(object):
     __slots__ = ("adv_ref", "adv_ver", "ori_ref", "ori_ver", "adv_c", "ori_c", "d1", "jstar", "d2", "istar",
-                 "red", "nbr", "kap", "hints")
+                 "red", "nbr", "kap", "hints", "arr")
 
     def matches(self, adv, ori):
         return (self.adv_ref() is adv and self.adv_ver == adv._version and self.ori_ref() is ori
@@ -150,7 +150,7 @@ def _entry(adv, ori, hints=None):
     e.adv_ref, e.adv_ver = weakref.ref(adv), adv._version
     e.ori_ref, e.ori_ver = weakref.ref(ori), ori._version
     e.adv_c, e.ori_c = _as_input(adv, "adv_pc"), _as_input(ori, "ori_pc")
-    e.d1 = e.jstar = e.d2 = e.istar = e.red = None
+    e.d1 = e.jstar = e.d2 = e.istar = e.red = e.arr = None
     e.nbr, e.kap = {}, {}
     _CACHE.append(e)
     if len(_CACHE) > _CACHE_MAX:
@@ -203,9 +203,10 @@ def _nbr(e, k):
         elif hb is not None:
             buf = hb.nbr.get(k)
             if buf is None or buf.shape[:2] != e.adv_c.shape[::2]:
-                hb.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1)[0]  # first call: nothing to hint with
-            else:
-                _launch_knn_hinted(e, k, hb)
+                # first call: nothing to hint with — the plain sorted search seeds the buffer, the regular launch
+                # then rewrites it in its own (visiting) order, so step 0 sums kappa in the same order as every later step
+                hb.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1)[0]
+            _launch_knn_hinted(e, k, hb)
             e.nbr[k] = hb.nbr[k]
         else:
             key = (e.adv_c.device,) + tuple(e.adv_c.shape) + (k,)
@@ -223,19 +224,35 @@ def _launch_nn_hinted(e, hb):
     hb.ensure_nn(b, n, m, e.adv_c.device)
     if n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
         hb.ensure_order(e.ori_c)
+        # ONE launch arranges adv into the visiting order and boxes its groups: both pruned searches of the step use it
+        e.arr = ops.arrange(e.adv_c, hb.perm, with_bbox=True)
         ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, perm_a=hb.perm, perm_o=hb.perm,
-                    iperm_a=hb.iperm, iperm_o=hb.iperm, ori_arranged=hb.ori_arranged,
+                    iperm_a=hb.iperm, iperm_o=hb.iperm, ori_arranged=hb.ori_arranged, adv_arranged=e.arr[0],
                     out=(hb.d1, hb.jstar, hb.d2, hb.istar))
     else:
+        e.arr = None
         ops.nn_pair(e.adv_c, e.ori_c, hint_a2o=hb.jstar, hint_o2a=hb.istar, out=(hb.d1, hb.jstar, hb.d2, hb.istar))
     e.d1, e.jstar, e.d2, e.istar = hb.d1, hb.jstar, hb.d2, hb.istar
 
 
 def _launch_knn_hinted(e, k, hb):
+    """Neighbour lists of the curvature term, refreshed in place (hint and output are the same buffer).  kappa and its
+    gradient only sum over the neighbourhood, so clouds that fit one staged chunk use the member-set kernel
+    (geoa3_knn_set: same members, visiting order) on the arrangement nn_pair already made this step; larger clouds
+    keep the sorted scan, box-pruned where that was measured to pay (n >= 2048, K <= 17)."""
     buf = hb.nbr[k]
-    if (hb.perm is not None and k <= 16 and e.adv_c.shape[2] >= hb.prune_min_n_knn
-            and e.adv_c.shape[2] == hb.perm.shape[1]):  # measured: pays for n >= 2048 and K <= 17 only
-        ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, perm_q=hb.perm, perm_c=hb.perm, iperm_c=hb.iperm)
+    n = e.adv_c.shape[2]
+    ordered = hb.perm is not None and n == hb.perm.shape[1]
+    arr = getattr(e, "arr", None)
+    if n <= 2048:
+        if ordered and arr is not None:
+            ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, perm_q=hb.perm, perm_c=hb.perm, iperm_c=hb.iperm,
+                    arranged=arr, members_only=True)
+        else:
+            ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, members_only=True)
+    elif ordered and k <= 16 and n >= hb.prune_min_n_knn:
+        ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf, perm_q=hb.perm, perm_c=hb.perm, iperm_c=hb.iperm,
+                arranged=arr)
     else:
         ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=buf, out=buf)
 
@@ -263,7 +280,7 @@ def step_plan(adv, ori, ori_normal, ori_kappa, k, hints, w=(1.0, 0.1, 1.0)):
     e.adv_ref = e.ori_ref = lambda: None
     e.adv_ver = e.ori_ver = -1
     e.adv_c, e.ori_c = _as_input(adv, "adv_pc"), _as_input(ori, "ori_pc")
-    e.d1 = e.jstar = e.d2 = e.istar = e.red = None
+    e.d1 = e.jstar = e.d2 = e.istar = e.red = e.arr = None
     e.nbr, e.kap = {}, {}
     nrm_src = _as_input(ori_normal, "ori_normal")
     ko = ori_kappa.detach().float().contiguous()

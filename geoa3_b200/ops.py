@@ -129,12 +129,14 @@ def group_bbox(pc_arranged):
 
 
 def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=None, perm_c=None, iperm_c=None,
-        arranged=None):
+        arranged=None, members_only=False):
     """query [b,3,n], ref [b,3,m] -> idx [b,n,K-drop] i32 (ascending (dist,idx)), dist | None.
     hint [b,n,hk] int32 (optional) only tightens the start threshold (exact for any hint); `out` may be the
     hint tensor itself (in-place refresh).  perm_* / iperm_c: visiting order for the pruned search;
     arranged = (cloud in that order, its boxes) from `arrange(..., with_bbox=True)` for a self-query whose
-    arrangement already exists this step."""
+    arrangement already exists this step.
+    members_only=True: the same K-drop members in ascending visiting order instead of by distance (geoa3_knn_set:
+    for consumers that only sum over the neighbourhood; ~2x cheaper)."""
     require_cuda_f32(query, "query"); require_cuda_f32(ref, "ref")
     b, _, n = query.shape
     m = ref.shape[2]
@@ -156,8 +158,9 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=No
     dist = torch.empty(b, n, K - drop, device=query.device, dtype=torch.float32) if return_dist else None
     with _guard(query):
         _count(1)
-        check(_lib.load().geoa3_knn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(perm_q), ptr(perm_c), ptr(iperm_c),
-                                    ptr(bb), ptr(hint), hk, ptr(idx), ptr(dist), stream(query)))
+        fn = _lib.load().geoa3_knn_set if members_only else _lib.load().geoa3_knn
+        check(fn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(perm_q), ptr(perm_c), ptr(iperm_c), ptr(bb), ptr(hint), hk,
+                 ptr(idx), ptr(dist), stream(query)))
     return idx, dist
 
 

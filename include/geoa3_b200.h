@@ -90,6 +90,16 @@ GEOA3_API int geoa3_knn(const float *query, const float *ref, int b, int n, int 
                         const int32_t *perm_q, const int32_t *perm_c, const int32_t *iperm_c, const float *bb_c,
                         const int32_t *hint, int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
 
+/* The same K - drop members as geoa3_knn (bit-exact membership: the K lexicographically smallest
+ * (pinned distance, index) pairs minus the `drop` smallest), written in ascending VISITING order of the candidates
+ * (ascending index without perm_c) instead of by distance — for consumers that sum over the neighbourhood (kappa and
+ * its gradient, Lib/loss_utils.py:59-62,79-82) and never look at the order.  Not sorting makes it ~2x cheaper.
+ * Arguments as geoa3_knn; `dist` (optional) receives the members' distances in the same order.
+ * Replaces: knn_points(pc, pc, K=k+1).idx[..., 1:] inside _get_kappa_adv / _get_kappa_ori, Lib/loss_utils.py:57-58,77-78. */
+GEOA3_API int geoa3_knn_set(const float *query, const float *ref, int b, int n, int m, int K, int drop,
+                            const int32_t *perm_q, const int32_t *perm_c, const int32_t *iperm_c, const float *bb_c,
+                            const int32_t *hint, int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
+
 /* Bounding boxes of a cloud that is already arranged in visiting order: per cloud geoa3_group_bbox_floats(n)
  * floats = [G0 + G1][8] (lo xyz, hi xyz, max |p|^2, pad), G0 = ceil(n/32) boxes of 32 consecutive positions
  * followed by G1 = ceil(n/1024) boxes of 1024.  Input to geoa3_knn's `bb_c` (required with perm_c): whole

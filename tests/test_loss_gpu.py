@@ -247,22 +247,39 @@ def test_hints_never_change_results():
 
 
 def test_attack_state_hints_match_unhinted():
+    """The persistent hint buffers of the attack are accelerators only.  (i) WHAT they hold never matters: buffers
+    carried over from the previous step, buffers left behind by a different batch and freshly initialised buffers
+    give bitwise identical losses and gradients.  (ii) Against the plain reference API (no buffers: neighbour lists
+    sorted by distance instead of in visiting order) the 1-NN indices and the neighbour SETS are identical; the
+    kappa sums run in a different order, so values agree to rounding (1e-6), not bitwise."""
     from geoa3_b200 import loss_utils as L
+    from geoa3_b200 import ops
 
     adv, ori, nrm = make(4, 1024, 7, 1e-2)
+    other = make(4, 1024, 11, 5e-2)[0]
     ko = L._get_kappa_ori(cu(ori), cu(nrm), 16)
-    hb = L.HintBuffers()
-    outs = []
+    hb, hb_stale = L.HintBuffers(), L.HintBuffers()
     for step in range(3):
         a_np = adv + synth.make_offsets(4, 1024, seed=10 + step, std=2e-3)
+        # hb_stale saw an unrelated cloud last: its indices are valid seeds, but useless ones
+        L.geo_loss(cu(other), cu(ori), cu(nrm), ko, 16, 1.0, 0.1, 1.0, hints=hb_stale)
         res = []
-        for hints in (hb, None):
+        for hints in (hb, hb_stale, L.HintBuffers(), None):
             L.clear_cache()
             a = cu(a_np).requires_grad_(True)
             tot, cd, hd, cv = L.geo_loss(a, cu(ori), cu(nrm), ko, 16, 1.0, 0.1, 1.0, hints=hints)
             tot.sum().backward()
             res.append((tot.detach().clone(), a.grad.clone()))
-        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        for r in res[1:3]:
+            assert torch.equal(res[0][0], r[0]) and torch.equal(res[0][1], r[1])
+        assert rel_err(res[0][0].cpu().numpy(), res[3][0].cpu().numpy()) < 1e-6
+        assert rel_err(res[0][1].cpu().numpy(), res[3][1].cpu().numpy()) < 1e-6
+        A = cu(a_np)
+        d1, j1, d2, i2 = ops.nn_pair(A, cu(ori))
+        assert torch.equal(hb.jstar, j1) and torch.equal(hb.istar, i2) and torch.equal(hb_stale.jstar, j1)
+        want = ops.knn(A, A, 17, drop=1)[0].sort(-1)[0]
+        assert torch.equal(hb.nbr[16].sort(-1)[0], want) and torch.equal(hb_stale.nbr[16].sort(-1)[0], want)
+        assert torch.equal(hb.nbr[16], hb_stale.nbr[16])   # same order, whatever the hint was
 
 
 @pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (1e-3, 0.0), (1e3, 0.0), (1.0, 50.0), (1e-2, 7.0), (30.0, -200.0)])
@@ -532,3 +549,63 @@ def test_pca_estimators_vs_reference_golden():
     moved = pc + synth.make_offsets(2, 400, std=2e-2)
     est = U.estimate_normal_via_ori_normal(cu(moved), cu(pc), cu(nr), 3).cpu().numpy()
     assert np.allclose(np.linalg.norm(est, axis=1), 1.0, atol=1e-4) and np.median(np.abs((est * nr).sum(1))) > 0.95
+
+
+def test_knn_set_members_exact():
+    """geoa3_knn_set (the neighbour lists of the curvature term): bit-exact MEMBERSHIP and member distances against
+    the oracle's top-K (minus the dropped self match) for every kind of hint and visiting order, on smooth clouds,
+    lattice ties, duplicated points, ragged sizes, multi-chunk clouds and clouds with fewer points than the list
+    capacity; the order it writes (ascending visiting position) does not depend on the hint."""
+    from geoa3_b200 import ops
+
+    rng = np.random.default_rng(5)
+    lat, _ = synth.lattice_cloud(343)
+    dup = make(2, 300, 4, 1e-2)[0]
+    dup[:, :, 150:200] = dup[:, :, 0:50]
+    cases = [(make(3, 1024, 2, 2e-2)[0], 17), (make(2, 1024, 1, 1e-2)[0], 33), (make(2, 777, 5, 5e-2)[0], 9),
+             (np.stack([lat, lat * 0.5]), 9), (np.ascontiguousarray(dup), 17), (make(1, 2500, 3, 1e-2)[0], 17),
+             (make(2, 40, 0, 1e-1)[0], 33), (make(2, 20, 0, 1e-1)[0], 17)]
+    for pts, K in cases:
+        b, _, n = pts.shape
+        K = min(K, n)
+        P = cu(pts)
+        oi, od = O.knn(pts, pts, K)
+        want_i, want_d = oi[:, :, 1:], od[:, :, 1:]
+
+        def check(idx, dist, tag):
+            i_, d_ = idx.cpu().numpy(), dist.cpu().numpy()
+            key = d_.view(np.int32).astype(np.int64) * 65536 + i_
+            o = np.argsort(key, -1)
+            assert np.array_equal(np.take_along_axis(i_, o, -1), want_i), (n, K, tag)
+            assert np.array_equal(np.take_along_axis(d_, o, -1), want_d), (n, K, tag)
+
+        exact = cu(want_i)
+        stale = cu(O.knn(pts + 0.05, pts[:, :, ::-1].copy(), K)[0][:, :, 1:])
+        junk = cu(rng.integers(-3, n + 50, (b, n, K - 1)).astype(np.int32))
+        zeros = torch.zeros(b, n, K - 1, dtype=torch.int32, device="cuda")
+        base = ops.knn(P, P, K, drop=1, return_dist=True, members_only=True)
+        check(*base, "unhinted")
+        pm, ipm = ops.visit_order(P)
+        pr = cu(np.stack([rng.permutation(n) for _ in range(b)]).astype(np.int32))
+        ipr = torch.empty_like(pr)
+        ipr.scatter_(1, pr.long(), torch.arange(n, device="cuda", dtype=torch.int32).expand(b, n).contiguous())
+        for h, tag in ((exact, "exact"), (stale, "stale"), (junk, "junk"), (zeros, "dup")):
+            idx, dist = ops.knn(P, P, K, drop=1, return_dist=True, hint=h, members_only=True)
+            check(idx, dist, tag)
+            assert torch.equal(idx, base[0]), (n, K, tag, "order depends on the hint")
+            for perm, iperm, ptag in ((pm, ipm, "visit"), (pr, ipr, "random")):
+                i2, d2 = ops.knn(P, P, K, drop=1, return_dist=True, hint=h, perm_q=perm, perm_c=perm, iperm_c=iperm,
+                                 members_only=True)
+                check(i2, d2, tag + "+" + ptag)
+        # in place: the buffer is hint and output at once, three refreshes of a moving cloud
+        buf, cur = exact.clone(), pts
+        for step in range(3):
+            cur = (cur + synth.make_offsets(b, n, seed=40 + step, std=3e-3)).astype(np.float32)
+            C = cu(cur)
+            ops.knn(C, C, K, drop=1, hint=buf, out=buf, perm_q=pm, perm_c=pm, iperm_c=ipm, members_only=True)
+            assert np.array_equal(np.sort(buf.cpu().numpy(), -1), np.sort(O.knn(cur, cur, K)[0][:, :, 1:], -1))
+    # drop=0 and a cross query (query cloud != candidate cloud)
+    q, c = make(2, 333, 2, 1e-1)[0], make(2, 777, 6, 1e-2)[0]
+    oi, od = O.knn(q, c, 5)
+    idx, dist = ops.knn(cu(q), cu(c), 5, drop=0, return_dist=True, members_only=True)
+    assert np.array_equal(np.sort(idx.cpu().numpy(), -1), np.sort(oi, -1))
