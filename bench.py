@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline + strong only (skip configs[2..4], baselines)")
     ap.add_argument("--msg-total", type=int, default=MSG_TOTAL)
+    ap.add_argument("--no-fold-bn", action="store_true", help="attack the victim as built (eval-mode BatchNorm kept as layers)")
     return ap.parse_args()
 
 
@@ -167,16 +168,22 @@ def ncu_traffic():
         return {}
 
 
+FOLD_BN = True
+
+
 def build_state(arch, b, n, row0, global_batch, dev, rows=None, graph=True):
-    """Victim + AttackState for rows [row0, row0+b) of a `global_batch`-row attack, step captured."""
+    """Victim + AttackState for rows [row0, row0+b) of a `global_batch`-row attack — exactly what the public
+    attack() sets up: parameters frozen, eval-mode BatchNorm folded into the conv / linear weights."""
     from geoa3_b200 import attack as atk
-    from geoa3_b200.victims import build_victim
+    from geoa3_b200.victims import build_victim, fold_batchnorm
 
     torch.manual_seed(0)
     net = build_victim(arch).to(dev).eval()
+    pc_h, nr_h, lab_h = make_inputs(b, n, row0)
+    if FOLD_BN:
+        net = fold_batchnorm(net, torch.from_numpy(pc_h[:2]).to(dev))
     for p in net.parameters():
         p.requires_grad_(False)
-    pc_h, nr_h, lab_h = make_inputs(b, n, row0)
     pc_pin, nr_pin = torch.from_numpy(pc_h).pin_memory(), torch.from_numpy(nr_h).pin_memory()
     off_pin = atk.default_offsets(global_batch, n, 0, 0, rows if rows is not None else range(row0, row0 + b)).pin_memory()
     target = torch.from_numpy(lab_h).to(dev)
@@ -463,7 +470,9 @@ def workload_config(args, world):
                         % (args.arch, NPTS, args.batch, KNN),
             "global_batch": args.batch * world, "npoint": NPTS, "parallelism": "instance-sharded x%d, no data-path collective" % world,
             "l2": "per-step working set (victim activations ~1 GB at B=250) exceeds the 126 MB L2; no explicit flush",
-            "cuda_graph": not args.no_graph}
+            "cuda_graph": not args.no_graph,
+            "victim": "random-init, eval mode, parameters frozen, BatchNorm folded into conv/linear weights (exact algebra)"
+                      if not args.no_fold_bn else "random-init, eval mode, parameters frozen"}
 
 
 # ------------------------------------------------------------------ strong-scaling records
@@ -655,6 +664,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    global FOLD_BN
+    FOLD_BN = not args.no_fold_bn
 
     from geoa3_b200 import dist as gdist
     from geoa3_b200 import loss_utils

@@ -157,7 +157,8 @@ class AttackState(object):
         self.loss_log = torch.zeros(_get(cfg, "iter_max_steps"), b, **f)
         self.last = {}
         if _get(cfg, "optim") == "adam":
-            self.opt = torch.optim.Adam([self.offset], lr=_get(cfg, "lr"), capturable=True)
+            # one fused, graph-capturable launch per step (the default foreach implementation is ~15 launches)
+            self.opt = torch.optim.Adam([self.offset], lr=_get(cfg, "lr"), capturable=True, fused=self.offset.is_cuda)
         elif _get(cfg, "optim") == "sgd":  # the partial-variable branch uses momentum 0.9 (:250), the plain one none (:270)
             self.opt = torch.optim.SGD([self.offset], lr=_get(cfg, "lr"),
                                        momentum=0.9 if _get(cfg, "is_partial_var") else 0.0)
@@ -395,14 +396,16 @@ class frozen_parameters(object):
 
 
 def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=False, use_cuda_graph=True,
-           global_batch=None, rows=None, seed=0, device=None, return_state=False):
+           global_batch=None, rows=None, seed=0, device=None, return_state=False, fold_bn=True):
     """Drop-in for geoA3_attack.attack(net, input_data, cfg, i, loader_len, saved_dir).
 
     Extra keyword arguments (all optional): `global_batch` / `rows` describe the shard of a larger batch
     this process owns (loss scaling + initial offsets), `use_cuda_graph` replays the captured step,
     `ref_quirks=True` reproduces the reference's stale-`output_label` coupling in the scale-const update (:375;
     the default implements the evident per-instance intent — see INTEGRATION.md section 4), `return_state=True`
-    appends the AttackState (device-side per-instance statistics for dist.attack_sharded).
+    appends the AttackState (device-side per-instance statistics for dist.attack_sharded), `fold_bn=True` attacks a
+    copy of the (eval-mode) victim whose BatchNorm layers are folded into the preceding conv / linear weights
+    (victims.fold_batchnorm: exact algebra, logits equal to rounding, a third of the PointNet step saved).
     The victim's parameters are frozen for the duration of the call (no weight-gradient kernels) and restored."""
     device = device or torch.device("cuda", torch.cuda.current_device())
     targeted = _get(cfg, "attack_label") != "Untarget"
@@ -410,6 +413,11 @@ def attack(net, input_data, cfg, i=0, loader_len=1, saved_dir=None, ref_quirks=F
     b, _, n = pc_ori.shape
     gb = global_batch if global_batch is not None else b
     steps = _get(cfg, "iter_max_steps")
+    if fold_bn and not net.training:
+        from .victims import fold_batchnorm
+
+        net = fold_batchnorm(net, pc_ori[:2] if not (_get(cfg, "is_subsample_opt") and n > _get(cfg, "npoint"))
+                             else pc_ori[:2, :, :_get(cfg, "npoint")].contiguous())
     with frozen_parameters(net):
         st = AttackState(net, pc_ori, normal_ori, target, gt_target, cfg, targeted, global_batch=gb)
         graphable = use_cuda_graph and not _get(cfg, "is_use_lr_scheduler") and not st.subsample and not st.partial and not st.jitter_on  # (host-side random picks / periods)

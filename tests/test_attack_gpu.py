@@ -231,3 +231,40 @@ def test_attack_flag_matrix(kw):
     if "cc_linf" in kw:
         assert float((out[0] - torch.from_numpy(synth.make_batch(3, 256)[0]).cuda()).abs().max()) <= 0.02 + 1e-6 \
             or not out[2].any()
+
+
+def test_fold_batchnorm_and_frozen_parameters():
+    """attack() runs on a BatchNorm-folded copy of the eval-mode victim with its parameters frozen (no weight-gradient
+    kernels); the caller's module is left exactly as it was.  Folding is exact algebra: logits and the first-step
+    losses agree with the unfolded victim to rounding."""
+    from geoa3_b200 import attack as atk
+    from geoa3_b200.victims import build_victim, fold_batchnorm
+
+    torch.manual_seed(3)
+    for arch, n in (("PointNet", 512), ("PointNetPP_ssg", 1024)):
+        net = build_victim(arch).cuda().eval()
+        for m in net.modules():  # non-trivial running statistics
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+                m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
+        x = torch.from_numpy(synth.make_batch(3, n, 1)[0]).cuda()
+        folded = fold_batchnorm(net, x[:2])
+        assert not any(isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)) for m in folded.modules())
+        tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                a, b_ = net(x), folded(x)
+            assert float((a - b_).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
+            before = {k: v.clone() for k, v in net.state_dict().items()}
+            data = _data(3, n)
+            cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=2, curv_loss_knn=8)
+            l_fold = np.asarray(atk.attack(net, data, cfg, use_cuda_graph=False, fold_bn=True)[4])
+            l_plain = np.asarray(atk.attack(net, data, cfg, use_cuda_graph=False, fold_bn=False)[4])
+            assert np.allclose(l_fold[0], l_plain[0], rtol=2e-5, atol=1e-6)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        assert all(p.requires_grad for p in net.parameters())           # restored
+        assert all(p.grad is None for p in net.parameters())            # and never differentiated
+        after = net.state_dict()
+        assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
