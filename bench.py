@@ -87,16 +87,19 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken inside the wall-clock window [t0, t1] (the timed region); nvidia-smi needs a
+        few hundred ms to deliver its first sample, so the sampler is started well before the window opens."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (ts, r) in self.rows if t0 is None or (t0 - 0.05 <= ts <= t1 + 0.15)]
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for nme, v in zip(names, r[5:9]):
@@ -212,13 +215,16 @@ def timed_steps(st, steps, warmup, dev, gdist, tail=None):
     """W warm-up + K timed steps (+ optional tail() inside the timed region); device time, max over ranks (ms)."""
     for _ in range(warmup):
         st.run_step()
+    st.step_idx.zero_()  # (the per-step loss log has iter_max_steps rows: keep its row index inside it)
     torch.cuda.synchronize()
     gdist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(steps):
+    for i in range(steps):
         st.run_step()
+        if (i + 1) % 400 == 0:
+            st.step_idx.zero_()
     out = tail() if tail is not None else None
     e1.record()
     torch.cuda.synchronize()
@@ -227,19 +233,19 @@ def timed_steps(st, steps, warmup, dev, gdist, tail=None):
 
 
 # ------------------------------------------------------------------ loss-path kernels
-def kernel_breakdown(pc_ori, nrm, adv, k):
+def kernel_breakdown(pc_ori, nrm, prev_adv, adv, k):
     """CUDA-event time of each own kernel of the loss path at the bench batch (µs, mean of 10), in the exact
-    configuration the attack step launches them (loss_utils._GeoLoss with HintBuffers): 1-NN seeded and slab-arranged,
-    kNN hinted with the previous step's neighbours (here: of a cloud one Adam step away)."""
+    configuration the attack step launches them (loss_utils._GeoLoss with HintBuffers) and on the state a REAL attack
+    produces: `prev_adv` and `adv` are the clouds of two consecutive Adam steps of the timed run, the search hints are
+    the indices found on `prev_adv` (kept frozen, so every repetition sees the same previous-step hints)."""
     from geoa3_b200 import loss_utils as L
-    from geoa3_b200 import ops
 
     b, _, n = adv.shape
-    prev = (adv - 0.003 * torch.sign(torch.randn_like(adv))).contiguous()
     hb = L.HintBuffers()
     ko = L._get_kappa_ori(pc_ori, nrm, k).detach()
-    plan = L.step_plan(prev, pc_ori, nrm, ko, k, hb)      # fills the hint buffers from the previous cloud
-    plan = L.step_plan(adv, pc_ori, nrm, ko, k, hb)       # the calls of one steady-state step, as closures
+    L.step_plan(prev_adv, pc_ori, nrm, ko, k, hb)         # fills the hint buffers from the previous step's cloud
+    hb.frozen = {"jstar": hb.jstar.clone(), "istar": hb.istar.clone(), "nbr": {k: hb.nbr[k].clone()}}
+    plan = L.step_plan(adv, pc_ori, nrm, ko, k, hb)       # the launches of one steady-state step, as closures
     g = torch.full((b,), 1.0 / b, device=adv.device)
     t = {}
     for name, fn in plan["launches"](g):
@@ -582,17 +588,37 @@ def headline(args, rank, local_rank, world, dev, gdist):
     from geoa3_b200 import loss_utils
 
     b, n = args.batch, NPTS
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     st, (pc_pin, nr_pin, off_pin) = build_state(args.arch, b, n, rank * b, b * world, dev)
     pc_ori, nrm = st.pc_ori, st.normal_ori
     launches_per_step = count_and_capture(st, off_pin.to(dev), graph=not args.no_graph)
 
     # ---------------- device-resident timing: W warm-up + K timed steps
-    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         st.run_step()
-    sampler.start()
+    torch.cuda.synchronize()
+    w0 = time.time()
     ms_total, _ = timed_steps(st, args.steps, 0, dev, gdist)
-    clocks = sampler.stop()
+    w1 = time.time()
+    # the clock record covers the timed region; short regions are extended by untimed steps so nvidia-smi (100 ms
+    # period) gets at least a few samples under the same load
+    st.step_idx.zero_()
+    while time.time() - w0 < 0.6:
+        st.run_step()
+        torch.cuda.synchronize()
+        w1 = time.time()
+    st.step_idx.zero_()
+    clocks = sampler.stop(w0, w1)
+    # two consecutive clouds of this run (>= 60 Adam steps in: past the first steps, where every point still moves by
+    # the full learning rate) for the per-kernel timings below
+    for _ in range(max(0, 60 - args.warmup - args.steps)):
+        st.run_step()
+    prev_adv = (pc_ori + st.offset).detach().clone()
+    st.run_step()
+    adv = (pc_ori + st.offset).detach().clone()
+    steps_in = int(st.step_idx.item())
+    st.step_idx.zero_()
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
     final_loss = float(st.last["loss"].item())
@@ -655,8 +681,8 @@ def headline(args, rank, local_rank, world, dev, gdist):
             "gpu_launches": launches_per_step * args.steps,
             "instance_iters_per_s": value * b, "final_loss": final_loss}
 
-    adv = (pc_ori + st.offset).detach().contiguous()
-    return line, adv, pc_ori.clone(), nrm.clone()
+    line["loss_kernels_timed_at_step"] = steps_in
+    return line, (prev_adv, adv), pc_ori.clone(), nrm.clone()
 
 
 
@@ -696,7 +722,7 @@ def main():
 
     if rank == 0:
         # ---------------- roofline of the dominant own kernel, measured live (CUDA events, current stream)
-        kb = kernel_breakdown(pc_keep, nrm_keep, adv, KNN)
+        kb = kernel_breakdown(pc_keep, nrm_keep, adv[0], adv[1], KNN)
         pk = peaks()
         top = max(kb, key=kb.get)
         alg_bytes = {"arrange": 28 * b * n, "nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n,
@@ -716,7 +742,7 @@ def main():
                                        hbm_frac_of_52BN=round(52 * b * n / (sum(kb.values()) * 1e-6) / 1e9 / pk["hbm_gbs"], 5))
         if world == 1 and not args.no_extras:
             guarded("gpu_reference_loss_us", lambda: {
-                "dense_torch_loss_fwd_bwd_us": dense_torch_loss_us(pc_keep, nrm_keep, adv, KNN),
+                "dense_torch_loss_fwd_bwd_us": dense_torch_loss_us(pc_keep, nrm_keep, adv[1], KNN),
                 "what": "CD + 0.1*HD + curvature(k=16) forward+backward at B=%d, N=%d with the dense [b,n,n] + topk "
                         "formulation of Lib/loss_utils.py:30-31,54-56,67-69 in plain torch on this B200" % (b, n)})
             torch.cuda.empty_cache()
