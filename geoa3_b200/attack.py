@@ -285,7 +285,7 @@ class AttackState(object):
                 self.offset.copy_(lp_clip(self.offset, _get(cfg, "cc_linf")))
             self.step_idx.add_(1)
         self.last = dict(loss=loss.detach(), cls=cls_loss.detach(), dis=dis.detach(), hd=hd.detach(), curv=cu.detach(),
-                         constrain=constrain.detach())
+                         constrain=constrain.detach(), adv=input_curr.detach())  # adv: the cloud this step's losses saw
 
     def _new_region(self):
         """Start of a 50-step period of the partial-variable attack (eager only: host-side random seed point)."""

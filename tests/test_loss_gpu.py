@@ -609,3 +609,145 @@ def test_knn_set_members_exact():
     oi, od = O.knn(q, c, 5)
     idx, dist = ops.knn(cu(q), cu(c), 5, drop=0, return_dist=True, members_only=True)
     assert np.array_equal(np.sort(idx.cpu().numpy(), -1), np.sort(oi, -1))
+
+
+@pytest.mark.parametrize("path", golden_files())
+def test_gradient_elementwise_tolerance(path):
+    """north_star's 1e-5 RELATIVE on every gradient entry, not only norm-wise: |got - ref| <= 1e-5*|ref| for entries
+    down to 1 % of the cloud's largest, with the absolute floor 1e-5 * 1e-2 * max|ref| below that (helpers.elem_err).
+    Reference = the fp64 autograd gradient of the reference's own functions (golden fixtures)."""
+    from helpers import elem_err
+
+    from geoa3_b200 import loss_utils as L
+
+    g = np.load(path)
+    k = int(g["k"])
+    L.clear_cache()
+    adv = cu(g["adv"]).requires_grad_(True)
+    ori, nrm = cu(g["ori"]), cu(g["normal"])
+    ko = L._get_kappa_ori(ori, nrm, k)
+    (L.chamfer_loss(adv, ori) + 0.1 * L.hausdorff_loss(adv, ori)
+     + L.curvature_loss(adv, ori, L._get_kappa_adv(adv, ori, nrm, k)[0], ko)).sum().backward()
+    got = adv.grad.cpu().numpy()
+    for c in range(got.shape[0]):   # per cloud: a big cloud must not lend its scale to a small one
+        assert elem_err(got[c], g["f64_grad"][c]) <= 1.0, (c, elem_err(got[c], g["f64_grad"][c]))
+    # the fused node delivers the same gradient under the same bound
+    L.clear_cache()
+    a2 = cu(g["adv"]).requires_grad_(True)
+    L.geo_loss(a2, ori, nrm, ko, k, 1.0, 0.1, 1.0, hints=L.HintBuffers())[0].sum().backward()
+    for c in range(got.shape[0]):
+        assert elem_err(a2.grad[c].cpu().numpy(), g["f64_grad"][c]) <= 1.0
+    for name, val in (("cd", L.chamfer_loss(adv, ori)), ("hd", L.hausdorff_loss(adv, ori))):
+        assert elem_err(val.detach().cpu().numpy(), g["f64_" + name], floor=0.0) <= 1.0, name
+    assert elem_err(L._get_kappa_adv(adv, ori, nrm, k)[0].detach().cpu().numpy(), g["f64_kappa_adv"]) <= 1.0
+
+
+def test_full_batch_index_parity_B250():
+    """BASELINE config[1]/[2] size, EVERY cloud against the C oracle (not a spot check): fused 1-NN both directions,
+    kNN K=17 (sorted kernel and member-set kernel), FPS 1024->512 and ball_query r=0.2 / nsample=64."""
+    from geoa3_b200 import ops
+
+    b, n = 250, 1024
+    pc, _, _ = synth.make_batch(50, n, 0)
+    ori = np.tile(pc, (5, 1, 1))
+    adv = (ori + synth.make_offsets(b, n, seed=3, std=1e-2)).astype(np.float32)
+    A, Oc = cu(adv), cu(ori)
+    d1, j1, d2, i2 = ops.nn_pair(A, Oc)
+    od1, oj1 = O.nn1(adv, ori)
+    od2, oi2 = O.nn1(ori, adv)
+    assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    pm, ipm = ops.visit_order(Oc)
+    d1p, j1p, d2p, i2p = ops.nn_pair(A, Oc, hint_a2o=j1, hint_o2a=i2, perm_a=pm, perm_o=pm, iperm_a=ipm, iperm_o=ipm)
+    assert torch.equal(j1p, j1) and torch.equal(i2p, i2) and torch.equal(d1p, d1)
+    oi, od = O.knn(adv, adv, 17)
+    idx, dist = ops.knn(A, A, 17, return_dist=True)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    hint = cu(O.knn(ori, ori, 17)[0][:, :, 1:])   # "previous step" = the unperturbed cloud
+    mem = ops.knn(A, A, 17, drop=1, hint=hint, perm_q=pm, perm_c=pm, iperm_c=ipm, members_only=True)[0]
+    assert np.array_equal(np.sort(mem.cpu().numpy(), -1), np.sort(oi[:, :, 1:], -1))
+    xyz = np.ascontiguousarray(adv.transpose(0, 2, 1))
+    X = cu(xyz)
+    fi = ops.furthest_point_sampling(X, 512)
+    ofi = O.fps(xyz, 512)
+    assert np.array_equal(fi.cpu().numpy(), ofi)
+    new = np.ascontiguousarray(np.take_along_axis(xyz, ofi[:, :, None].astype(np.int64).repeat(3, 2), 1))
+    bq = ops.ball_query(cu(new), X, 0.2, 64)
+    assert np.array_equal(bq.cpu().numpy(), O.ball_query(new, xyz, 0.2, 64))
+
+
+def test_graph_replay_final_buffers_match_oracle():
+    """60 replays of the captured attack step (persistent hint buffers refreshed in place, slab-ordered pruned
+    searches, the product configuration): the index buffers left behind by the LAST replay are the oracle's answer for
+    the cloud that replay saw — a stale-hint or replay-aliasing bug would need many steps to show and would show here."""
+    from geoa3_b200 import attack as atk
+    from geoa3_b200.victims import build_victim
+
+    torch.manual_seed(0)
+    net = build_victim("PointNet").cuda().eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    b, n, k = 6, 1024, 16
+    pc, nr, lab = synth.make_batch(b, n, 4)
+    dev = torch.device("cuda")
+    cfg = atk.make_cfg(binary_max_steps=1, iter_max_steps=100, curv_loss_knn=k)
+    lab_t = torch.from_numpy(lab).to(dev)
+    st = atk.AttackState(net, torch.from_numpy(pc).to(dev), torch.from_numpy(nr).to(dev), lab_t, lab_t, cfg, targeted=False)
+    init = atk.default_offsets(b, n, 0, 0).to(dev)
+    st.begin_search_step(0, init)
+    st.capture()
+    st.reset_global()
+    st.begin_search_step(0, init)
+    for _ in range(60):
+        st.run_step()
+    torch.cuda.synchronize()
+    adv = st.last["adv"].cpu().numpy()          # the cloud the last replay searched (before its Adam update)
+    assert np.abs(adv - pc).max() > 5e-3         # the optimisation really moved the cloud
+    od1, oj1 = O.nn1(adv, pc)
+    od2, oi2 = O.nn1(pc, adv)
+    hb = st.hints
+    assert np.array_equal(hb.jstar.cpu().numpy(), oj1) and np.array_equal(hb.istar.cpu().numpy(), oi2)
+    assert np.array_equal(hb.d1.cpu().numpy(), od1) and np.array_equal(hb.d2.cpu().numpy(), od2)
+    oi, _ = O.knn(adv, adv, k + 1)
+    assert np.array_equal(np.sort(hb.nbr[k].cpu().numpy(), -1), np.sort(oi[:, :, 1:], -1))
+    # and the loss values of that replay agree with the oracle on that cloud
+    ko, _ = O.kappa_ori(pc, nr, k)
+    fwd = O.geo_forward(adv, pc, nr, ko, k)
+    assert rel_err(st.last["dis"].cpu().numpy(), fwd["cd"]) < TOL and rel_err(st.last["hd"].cpu().numpy(), fwd["hd"]) < TOL
+    assert rel_err(st.last["curv"].cpu().numpy(), fwd["curv"]) < TOL
+
+
+@pytest.mark.parametrize("n,k", [(2970, 16), (3000, 16), (3740, 8), (3800, 8), (2690, 20), (2720, 20), (1024, 32)])
+def test_backward_fused_kernel_near_shared_memory_limit(n, k):
+    """Cloud sizes around the point where the fused backward's shared-memory plan stops fitting (its counter array used
+    to be sized for 16-bit counters although the CSR builder uses 32-bit ones — harmless at n = 1024, corrupting in
+    n = 2977..3055 at k = 16, 3745..3869 at k = 8, 2700..2763 at k = 20): the largest size that still takes the fused
+    kernel and a size inside each formerly corrupting range; gradient vs the oracle, bit-identical to the
+    global-workspace path."""
+    import os
+
+    from geoa3_b200 import loss_utils as L
+    from geoa3_b200 import ops
+
+    b = 2
+    adv, ori, nrm = make(b, n, 2, 2e-2)
+    fused = ops._lib.load().geoa3_loss_bwd_workspace_bytes(b, n, n, k) == 0
+    assert fused == ((n, k) in ((2970, 16), (3740, 8), (2690, 20), (1024, 32)))
+    ko = L._get_kappa_ori(cu(ori), cu(nrm), k)
+    grads = []
+    for env in (None, "1"):
+        if env:
+            os.environ["GEOA3_BWD_LARGE"] = env
+        try:
+            L.clear_cache()
+            a = cu(adv).requires_grad_(True)
+            L.geo_loss(a, cu(ori), cu(nrm), ko, k, 1.0, 0.1, 1.0)[0].sum().backward()
+            grads.append(a.grad.clone())
+        finally:
+            os.environ.pop("GEOA3_BWD_LARGE", None)
+    assert torch.equal(grads[0], grads[1])
+    ko_o, _ = O.kappa_ori(ori, nrm, k)
+    fwd = O.geo_forward(adv, ori, nrm, ko_o, k)
+    g = np.ones(b)
+    want = O.geo_backward(adv, ori, fwd, ko_o, g * 1.0, g * 0.1, g * 1.0)
+    assert rel_err(grads[0].cpu().numpy(), want) < TOL
