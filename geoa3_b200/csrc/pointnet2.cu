@@ -306,9 +306,11 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
   __syncthreads();
   const float r2 = __fmul_rn(radius, radius);
   const unsigned lt = (1u << lane) - 1u;
-  int* row = s_row[w];
   const int c_beg = (blockIdx.x * BQ_WARPS + w) * BQ_PER_WARP;
   for (int c = c_beg; c < min(m, c_beg + BQ_PER_WARP); ++c) {
+    int32_t* o = idx + ((size_t)cloud * m + c) * nsample;
+    // rows of more than BQ_MAX_NS samples (uniform_loss on dense clouds) are collected in the output row itself
+    int* row = nsample <= BQ_MAX_NS ? s_row[w] : o;
     const float* q = new_xyz + ((size_t)cloud * m + c) * 3;
     const float qx = -q[0], qy = -q[1], qz = -q[2];
     const float2 nqx = make_float2(qx, qx), nqy = make_float2(qy, qy), nqz = make_float2(qz, qz);
@@ -329,7 +331,6 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
     __syncwarp();
     cnt = min(cnt, nsample);
     const int first = cnt > 0 ? row[0] : 0;  // first-hit fill; a centroid with no hit keeps zeros
-    int32_t* o = idx + ((size_t)cloud * m + c) * nsample;
     for (int l = lane; l < nsample; l += 32) o[l] = l < cnt ? row[l] : first;
     __syncwarp();
   }
@@ -421,9 +422,9 @@ constexpr int GP_ETILE = 8192;   // (j,k) positions per CTA
 
 __global__ void __launch_bounds__(GP_THREADS)
 group_points_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx, int c, int n, int E,
-                    float* __restrict__ out) {
-  extern __shared__ __align__(16) float s_rows[];  // [cc][n]
-  const int cloud = blockIdx.z, c0 = blockIdx.y * GP_CC, cc = min(GP_CC, c - c0);
+                    float* __restrict__ out, int gcc) {
+  extern __shared__ __align__(16) float s_rows[];  // [cc][n]; gcc = channels per CTA (GP_CC unless n is very large)
+  const int cloud = blockIdx.z, c0 = blockIdx.y * gcc, cc = min(gcc, c - c0);
   const int tid = threadIdx.x;
   const float* src = points + ((size_t)cloud * c + c0) * n;
   // The cc feature rows of this CTA are ONE contiguous block of cc*n floats: when it is 16-byte aligned and sized,
@@ -1121,7 +1122,7 @@ extern "C" int geoa3_farthest_points_sample(const float* xyz, int b, int n, int 
 extern "C" int geoa3_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius,
                                 int nsample, int32_t* idx, geoa3_stream_t stream) {
   GEOA3_CHECK_ARG(new_xyz && xyz && idx && b > 0 && n > 0 && m > 0 && nsample > 0);
-  if (nsample > BQ_MAX_NS || b > 65535) return GEOA3_EUNSUPPORTED;
+  if (b > 65535) return GEOA3_EUNSUPPORTED;
   const size_t smem = (size_t)((n + 63) & ~63) * 12;
   if (smem > 200 * 1024) return GEOA3_EUNSUPPORTED;
   static PerDeviceOnce attr_done;
@@ -1130,7 +1131,7 @@ extern "C" int geoa3_ball_query(const float* new_xyz, const float* xyz, int b, i
     if (e != cudaSuccess) return (int)e;
     attr_done.done();
   }
-  if (n <= 65535 && !getenv("GEOA3_BQ_WARP")) {  // (env: A/B knob for tools/time_kernels.py, not part of the API)
+  if (n <= 65535 && nsample <= BQ_MAX_NS && !getenv("GEOA3_BQ_WARP")) {  // (env: A/B knob for tools/time_kernels.py, not part of the API)
     const size_t hs = (size_t)BQT_THREADS * (nsample + 2) * sizeof(uint16_t);
     static PerDeviceOnce attr_t;
     if (attr_t.needed()) {
@@ -1153,8 +1154,10 @@ extern "C" int geoa3_group_points(const float* points, const int32_t* idx, int b
   GEOA3_CHECK_ARG(points && idx && out && b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0);
   if (b > 65535 || (size_t)n * 4 * 1 > 200 * 1024) return GEOA3_EUNSUPPORTED;
   const int E = npoints * nsample;
-  // channels per CTA limited by shared memory (GP_CC rows of n floats)
-  const size_t smem = (size_t)(c < GP_CC ? c : GP_CC) * n * 4;
+  // channels per CTA limited by shared memory (GP_CC rows of n floats; fewer rows for very long ones)
+  int gcc = c < GP_CC ? c : GP_CC;
+  while (gcc > 1 && (size_t)gcc * n * 4 > 200 * 1024) gcc >>= 1;
+  const size_t smem = (size_t)gcc * n * 4;
   if (smem > 200 * 1024) return GEOA3_EUNSUPPORTED;
   static PerDeviceOnce attr_done;
   if (attr_done.needed()) {
@@ -1162,8 +1165,8 @@ extern "C" int geoa3_group_points(const float* points, const int32_t* idx, int b
     if (e != cudaSuccess) return (int)e;
     attr_done.done();
   }
-  dim3 grid(ceil_div(E, GP_ETILE), ceil_div(c, GP_CC), b);
-  group_points_kernel<<<grid, GP_THREADS, smem, (cudaStream_t)stream>>>(points, idx, c, n, E, out);
+  dim3 grid(ceil_div(E, GP_ETILE), ceil_div(c, gcc), b);
+  group_points_kernel<<<grid, GP_THREADS, smem, (cudaStream_t)stream>>>(points, idx, c, n, E, out, gcc);
   return GEOA3_LAUNCH_RESULT();
 }
 

@@ -55,7 +55,8 @@ def test_fps_ties_and_degenerate():
 
 
 @pytest.mark.parametrize("b,n,m,r,ns", [(10, 1024, 512, 0.2, 64), (10, 512, 128, 0.4, 64), (4, 1024, 512, 0.1, 16),
-                                        (4, 1024, 512, 0.4, 128), (2, 999, 77, 0.3, 33), (2, 100, 10, 0.01, 8)])
+                                        (4, 1024, 512, 0.4, 128), (2, 999, 77, 0.3, 33), (2, 100, 10, 0.01, 8),
+                                        (2, 10000, 500, 0.44, 480), (1, 6000, 64, 2.5, 300)])   # nsample > 256: uniform_loss on dense clouds
 def test_ball_query_bitexact(b, n, m, r, ns):
     from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
 
@@ -122,7 +123,8 @@ def test_fps_ulp_critical_vs_reference_binary():
                                           (2, 9, 512, 50, 32, 0.3), (2, 16, 1024, 37, 32, 0.12),
                                           (2, 10, 300, 33, 64, 0.08), (2, 6, 400, 21, 128, 0.5),
                                           (2, 13, 2048, 19, 64, 0.2),
-                                          (2, 5, 301, 20, 8, 0.3)])   # odd n: rows not 16-byte sized => plain staging
+                                          (2, 5, 301, 20, 8, 0.3),    # odd n: rows not 16-byte sized => plain staging
+                                          (1, 24, 10000, 40, 32, 0.15)])  # long rows: fewer channels staged per CTA
 def test_group_points_and_grad(b, c, n, m, ns, r):
     from geoa3_b200.pointnet2_ops import pointnet2_utils as pu
 
