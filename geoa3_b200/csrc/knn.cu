@@ -377,8 +377,8 @@ extern "C" int geoa3_knn_set(const float* query, const float* ref, int b, int n,
   GEOA3_CHECK_ARG(b > 0 && n > 0 && m > 0 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
   if (K > GEOA3_KNN_MAX_K || b > 65535) return GEOA3_EUNSUPPORTED;
   if (K > m) return GEOA3_EINVAL;
-  const int r = launch_knn_select(query, ref, b, n, m, K, K - drop, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx,
-                                  dist, (cudaStream_t)stream);
+  const int r = launch_knn_select(query, ref, b, n, m, K, K - drop, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx, dist,
+                                  (cudaStream_t)stream);
   if (r != INT_MIN) return r;
   // clouds beyond 65 535 points: the sorted list of geoa3_knn is one valid order of the same members
   return geoa3_knn(query, ref, b, n, m, K, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx, dist, stream);

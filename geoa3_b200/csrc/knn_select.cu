@@ -32,6 +32,9 @@
 #ifndef KS_THREADS_17
 #define KS_THREADS_17 128
 #endif
+#ifndef KS_EXTRA
+#define KS_EXTRA 11
+#endif
 
 namespace geoa3 {
 
@@ -41,7 +44,7 @@ constexpr float KS_MARGIN = 1.52587890625e-5f * 1.001f;  // 2^-16
 
 template <int K>
 struct KsCfg {
-  static constexpr int R = K + 7;                             // list slots per query
+  static constexpr int R = K + KS_EXTRA;                      // list slots per query
   static constexpr int THREADS = K <= 17 ? KS_THREADS_17 : 256;  // one query per thread
   static constexpr int MINB = K <= 17 ? 640 / THREADS : 2;     // resident CTAs that shared memory allows at n = 1024
 };

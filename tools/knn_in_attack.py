@@ -2,6 +2,7 @@
 Adam step apart), at several points of the optimisation.   python tools/knn_in_attack.py [--batch 250]  -> JSON lines"""
 import argparse
 import json
+import os
 import os.path as osp
 import sys
 
@@ -32,7 +33,7 @@ def t(fn, iters=5):
     return round(sorted(ts)[len(ts) // 2], 1)
 
 
-probe = {1, 2, 5, 20, 60, 150, 300, 499}
+probe = {1, 5, 20, 150, 499}
 for step in range(500):
     if step in probe and step > 0:
         hint = st.hints.nbr[k].clone()              # lists of the previous step
@@ -46,7 +47,8 @@ for step in range(500):
         move = float((adv - prev_adv).abs().max())
         new = ops.knn(adv, adv, k + 1, drop=1)[0]
         changed = float((new.sort(-1)[0] != hint.sort(-1)[0]).any(-1).float().mean())
-        r = dict(step=step, max_move=round(move, 5), rows_with_changed_set=round(changed, 3),
+        extra = {}
+        r = dict(step=step, max_move=round(move, 5), rows_with_changed_set=round(changed, 3), **extra,
                  set_pruned=t(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hint.clone(), perm_q=hb.perm, perm_c=hb.perm,
                                               iperm_c=hb.iperm, arranged=arr, members_only=True)),
                  set_hinted=t(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hint.clone(), members_only=True)),
