@@ -365,12 +365,15 @@ def sweep_record(dev):
             t_plain = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1), 3, 1)
             t_hint = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn), 3, 1)
             t_prune = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm), 3, 1)
+            t_set = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm,
+                                                members_only=True), 3, 1)
             nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
             t_kap = time_events(lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr), 3, 1)
-            best = min(t_hint, t_prune)
+            best = min(t_hint, t_prune, t_set)
             byts = (28 + 4 * k) * B * n
             rows.append({"n": n, "k": k, "knn_us": round(t_plain, 1), "knn_hinted_us": round(t_hint, 1),
-                         "knn_hinted_pruned_us": round(t_prune, 1), "kappa_us": round(t_kap, 1),
+                         "knn_hinted_pruned_us": round(t_prune, 1), "knn_members_hinted_pruned_us": round(t_set, 1),
+                         "kappa_us": round(t_kap, 1),
                          "hbm_frac": round(byts / ((best + t_kap) * 1e-6) / 1e9 / pk["hbm_gbs"], 5),
                          "fp32_tflops": round(8.0 * B * n * n / (best * 1e-6) / 1e12, 2)})
     return rows

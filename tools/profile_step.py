@@ -17,7 +17,11 @@ ap.add_argument("--steps", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 st, pins = bench.build_state(a.arch, a.batch, bench.NPTS, 0, a.batch, dev)
-for _ in range(a.steps):
+for _ in range(a.steps - 1):
     st.step()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures the last step only
+st.step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
