@@ -20,6 +20,11 @@ SIGNATURES = {
     "geoa3_nn_pair": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 11),
     "geoa3_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "geoa3_knn_set": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "geoa3_cell_grid_max": (_i, [_i]),
+    "geoa3_cell_blob_bytes": (_sz, [_i, _i]),
+    "geoa3_cell_sort": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "geoa3_knn_cells": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "geoa3_nn_pair_cells": (_i, [_vp, _vp, _i, _i, _i, _i, _i] + [_vp] * 7),
     "geoa3_group_bbox_floats": (_sz, [_i]),
     "geoa3_group_bbox": (_i, [_vp, _i, _i, _vp, _vp]),
     "geoa3_arrange": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -12,8 +12,8 @@ import sys
 HERE = osp.dirname(osp.abspath(__file__))
 CSRC = osp.join(HERE, "csrc")
 SO = osp.join(HERE, "libgeoa3_b200.so")
-SOURCES = ["nn_pair.cu", "knn.cu", "knn_select.cu", "kappa_loss.cu", "pointnet2.cu"]
-HEADERS = ["common.cuh", "csr.cuh", osp.join("..", "..", "include", "geoa3_b200.h")]
+SOURCES = ["nn_pair.cu", "knn.cu", "knn_select.cu", "knn_cells.cu", "nn_cells.cu", "kappa_loss.cu", "pointnet2.cu"]
+HEADERS = ["common.cuh", "csr.cuh", "cells.cuh", osp.join("..", "..", "include", "geoa3_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

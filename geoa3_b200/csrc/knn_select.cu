@@ -115,7 +115,7 @@ knn_select_kernel(const float* __restrict__ query, const float* __restrict__ ref
                   const int32_t* __restrict__ perm_q, const int32_t* __restrict__ perm_c,
                   const int32_t* __restrict__ iperm_c, const float* __restrict__ bb_c, const int32_t* hint, int hint_k,
                   int32_t* idx_out, float* __restrict__ dist_out, int cs, int kk) {
-  // kk = min(K, m): the list target (K is the compile-time capacity; a cloud may hold fewer than K points)
+  // kk = min(requested K, m): the list target (the template K is the capacity class; a cloud may hold fewer points)
   constexpr int R = KsCfg<K>::R;
   extern __shared__ __align__(16) unsigned char ks_smem[];
   float* sx = reinterpret_cast<float*>(ks_smem);
@@ -143,7 +143,7 @@ knn_select_kernel(const float* __restrict__ query, const float* __restrict__ ref
   const int qo = perm_q ? perm_q[(size_t)cloud * n + sl] : sl;  // ORIGINAL index of the query
   const bool live = slot < n;
   bool act = live;                        // still searching
-  const bool use_hint = hint != nullptr && hint_k + 1 >= K && (!PRUNE || ipc);
+  const bool use_hint = hint != nullptr && hint_k + 1 >= kk && (!PRUNE || ipc);
   const bool hint16 = use_hint && one_chunk && hint_k == 16 && ((reinterpret_cast<uintptr_t>(hint) & 15) == 0);
   int4 hreg[4];                           // hint row fetched up front: its DRAM/L2 latency hides behind the staging
   if (hint16) {
@@ -361,7 +361,7 @@ knn_select_kernel(const float* __restrict__ query, const float* __restrict__ ref
 }
 
 template <int K>
-static int launch_knn_select_k(const float* query, const float* ref, int b, int n, int m, int kout, int drop,
+static int launch_knn_select_k(const float* query, const float* ref, int b, int n, int m, int kreq, int kout, int drop,
                                const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const float* bb_c,
                                const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
   constexpr int T = KsCfg<K>::THREADS;
@@ -378,7 +378,7 @@ static int launch_knn_select_k(const float* query, const float* ref, int b, int 
       once.done();
     }
     knn_select_kernel<K, T, true><<<grid, T, smem, s>>>(query, ref, n, m, kout, drop, perm_q, perm_c, iperm_c, bb_c, hint,
-                                                      hint_k, idx, dist, cs, min(K, m));
+                                                      hint_k, idx, dist, cs, min(kreq, m));
   } else {
     static PerDeviceOnce once;
     if (once.needed()) {
@@ -387,7 +387,7 @@ static int launch_knn_select_k(const float* query, const float* ref, int b, int 
       once.done();
     }
     knn_select_kernel<K, T, false><<<grid, T, smem, s>>>(query, ref, n, m, kout, drop, perm_q, nullptr, nullptr, nullptr,
-                                                       hint, hint_k, idx, dist, cs, min(K, m));
+                                                       hint, hint_k, idx, dist, cs, min(kreq, m));
   }
   return GEOA3_LAUNCH_RESULT();
 }
@@ -397,7 +397,7 @@ int launch_knn_select(const float* query, const float* ref, int b, int n, int m,
                       const int32_t* perm_q, const int32_t* perm_c, const int32_t* iperm_c, const float* bb_c,
                       const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
   if (n > 65535 || m > 65535) return INT_MIN;
-#define GEOA3_KS_ARGS query, ref, b, n, m, kout, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx, dist, s
+#define GEOA3_KS_ARGS query, ref, b, n, m, K, kout, drop, perm_q, perm_c, iperm_c, bb_c, hint, hint_k, idx, dist, s
   if (K <= 3) return launch_knn_select_k<3>(GEOA3_KS_ARGS);
   if (K <= 5) return launch_knn_select_k<5>(GEOA3_KS_ARGS);
   if (K <= 9) return launch_knn_select_k<9>(GEOA3_KS_ARGS);

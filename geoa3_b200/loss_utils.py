@@ -56,9 +56,15 @@ class HintBuffers(object):
     the previous step's indices are such a seed.  The kernels read the hint and write the new result into
     the SAME buffer, so the hints stay fresh even when the whole step is replayed as a CUDA graph."""
 
-    def __init__(self, prune_min_n_knn=2048):
+    def __init__(self, prune_min_n_knn=2048, use_cells=True):
         self.d1 = self.jstar = self.d2 = self.istar = None
         self.nbr = {}
+        # cell-grid searches (geoa3_cell_sort / geoa3_nn_pair_cells / geoa3_knn_cells): the original cloud's blob is
+        # built once, the adversarial cloud's every step (one launch feeds the 1-NN and the kNN search).  Results are
+        # identical to the scanning kernels; use_cells=False keeps those (A/B measurements, tests).
+        self.use_cells = use_cells
+        self.knn_k = 16  # neighbourhood size the adversarial grid is sized for (set by the fused loss node)
+        self.cells_ori = self.cells_adv = None   # (blobs, G)
         # visiting order for the pruned searches (ops.visit_order of the ORIGINAL cloud), computed once (first call)
         self.perm = self.iperm = self.ori_arranged = None
         self.prune_min_n_knn = prune_min_n_knn  # measured: box pruning of the kNN scan only pays for larger clouds
@@ -75,12 +81,38 @@ class HintBuffers(object):
     def refresh_order(self, ori):
         """The original cloud's CONTENTS changed (AttackState.load_batch): recompute the visiting order into the
         existing tensors (their addresses are baked into a captured CUDA graph)."""
+        self.refresh_cells(ori)
         if self.perm is None or self.perm.shape != (ori.shape[0], ori.shape[2]):
             return  # nothing computed yet; ensure_order() will do it on first use
         perm, iperm = ops.visit_order(ori)
         self.perm.copy_(perm)
         self.iperm.copy_(iperm)
         self.ori_arranged.copy_(ops.arrange(ori, self.perm))
+
+    CELLS_MAX_N = 3072  # the kNN CTA stages blob + lists in shared memory with >= 2 CTAs per SM up to here
+
+    def cells_ok(self, n, m):
+        return self.use_cells and 32 <= n <= self.CELLS_MAX_N and 32 <= m <= self.CELLS_MAX_N
+
+    def ensure_cells(self, ori, k=16):
+        """Blob of the ORIGINAL cloud (static during an attack) + the buffer the adversarial blob is rebuilt into."""
+        b, _, m = ori.shape
+        if self.cells_ori is None or self.cells_ori[0].shape[0] != b or self.cells_ori[2] != m:
+            g = ops.cell_grid_size(m, 8)      # 1-NN balls are small: a finer grid than the kNN one (measured)
+            self.cells_ori = (ops.cell_sort(ori, g), g, m)
+
+    def refresh_cells(self, ori):
+        if self.cells_ori is not None and self.cells_ori[0].shape[0] == ori.shape[0] and self.cells_ori[2] == ori.shape[2]:
+            ops.cell_sort(ori, self.cells_ori[1], out=self.cells_ori[0])
+
+    def sort_adv(self, adv, k=16):
+        b, _, n = adv.shape
+        g = ops.cell_grid_size(n, k + 1)
+        if self.cells_adv is None or self.cells_adv[0].shape[0] != b or self.cells_adv[2] != n or self.cells_adv[1] != g:
+            self.cells_adv = (ops.cell_sort(adv, g), g, n)
+        else:
+            ops.cell_sort(adv, g, out=self.cells_adv[0])
+        return self.cells_adv
 
     def ensure_nn(self, b, n, m, dev):
         if self.jstar is None or self.jstar.shape != (b, n) or self.istar.shape != (b, m):
@@ -113,7 +145,7 @@ def _order_of(ori_obj, ori_c):
 # ---------------------------------------------------------------------------- per-step cache
 class _Entry(object):
     __slots__ = ("adv_ref", "adv_ver", "ori_ref", "ori_ver", "adv_c", "ori_c", "d1", "jstar", "d2", "istar",
-                 "red", "nbr", "kap", "hints", "arr")
+                 "red", "nbr", "kap", "hints", "arr", "cells")
 
     def matches(self, adv, ori):
         return (self.adv_ref() is adv and self.adv_ver == adv._version and self.ori_ref() is ori
@@ -154,7 +186,7 @@ def _entry(adv, ori, hints=None):
     e.adv_ref, e.adv_ver = weakref.ref(adv), adv._version
     e.ori_ref, e.ori_ver = weakref.ref(ori), ori._version
     e.adv_c, e.ori_c = _as_input(adv, "adv_pc"), _as_input(ori, "ori_pc")
-    e.d1 = e.jstar = e.d2 = e.istar = e.red = e.arr = None
+    e.d1 = e.jstar = e.d2 = e.istar = e.red = e.arr = e.cells = None
     e.nbr, e.kap = {}, {}
     _CACHE.append(e)
     if len(_CACHE) > _CACHE_MAX:
@@ -227,7 +259,16 @@ def _launch_nn_hinted(e, hb):
     m = e.ori_c.shape[2]
     hb.ensure_nn(b, n, m, e.adv_c.device)
     hj, hi = (hb.frozen["jstar"], hb.frozen["istar"]) if hb.frozen else (hb.jstar, hb.istar)
-    if n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
+    e.cells = None
+    if hb.cells_ok(n, m):
+        # cell-grid path: ONE launch sorts adv into its cell grid (also used by the kNN search of this step); each query
+        # then only meets the candidates within reach of the distance to last step's argmin
+        hb.ensure_cells(e.ori_c)
+        e.cells = hb.sort_adv(e.adv_c, hb.knn_k)
+        e.arr = None
+        ops.nn_pair_cells(e.cells[0], hb.cells_ori[0], n, m, e.cells[1], hb.cells_ori[1], hint_a2o=hj, hint_o2a=hi,
+                          out=(hb.d1, hb.jstar, hb.d2, hb.istar))
+    elif n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
         hb.ensure_order(e.ori_c)
         # ONE launch arranges adv into the visiting order and boxes its groups: both pruned searches of the step use it
         e.arr = ops.arrange(e.adv_c, hb.perm, with_bbox=True)
@@ -248,6 +289,10 @@ def _launch_knn_hinted(e, k, hb):
     buf = hb.nbr[k]
     hint = hb.frozen["nbr"][k] if hb.frozen else buf
     n = e.adv_c.shape[2]
+    cells = getattr(e, "cells", None)
+    if cells is not None and cells[1] == ops.cell_grid_size(n, k + 1):
+        ops.knn_cells(cells[0], n, cells[1], k + 1, drop=1, hint=hint, out=buf)
+        return
     ordered = hb.perm is not None and n == hb.perm.shape[1]
     arr = getattr(e, "arr", None)
     if n <= 2048:
@@ -286,8 +331,9 @@ def step_plan(adv, ori, ori_normal, ori_kappa, k, hints, w=(1.0, 0.1, 1.0)):
     e.adv_ref = e.ori_ref = lambda: None
     e.adv_ver = e.ori_ver = -1
     e.adv_c, e.ori_c = _as_input(adv, "adv_pc"), _as_input(ori, "ori_pc")
-    e.d1 = e.jstar = e.d2 = e.istar = e.red = e.arr = None
+    e.d1 = e.jstar = e.d2 = e.istar = e.red = e.arr = e.cells = None
     e.nbr, e.kap = {}, {}
+    hints.knn_k = k
     nrm_src = _as_input(ori_normal, "ori_normal")
     ko = ori_kappa.detach().float().contiguous()
     _launch_nn_hinted(e, hints)
@@ -381,6 +427,8 @@ class _GeoLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, adv_pc, ori_pc, ori_normal, ori_kappa, k, w_cd, w_hd, w_curv, single_side, hints):
+        if isinstance(hints, HintBuffers) and k > 0:
+            hints.knn_k = k
         e = _nn(_entry(adv_pc, ori_pc, hints), True)
         use_curv = w_curv != 0 and k > 0
         nbr = _nbr(e, k) if use_curv else None

@@ -1,6 +1,8 @@
 """Thin tensor-level wrappers over the C ABI (one Python function per entry point of
 include/geoa3_b200.h).  They allocate outputs with torch, launch on torch's current stream and raise
 RuntimeError on any non-zero return code.  No autograd here — see loss_utils.py / pointnet2_ops."""
+import math
+
 import torch
 
 from . import _lib
@@ -162,6 +164,62 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=No
         check(fn(ptr(query), ptr(ref), b, n, m, K, drop, ptr(perm_q), ptr(perm_c), ptr(iperm_c), ptr(bb), ptr(hint), hk,
                  ptr(idx), ptr(dist), stream(query)))
     return idx, dist
+
+
+def cell_grid_size(n, K):
+    """Cells per axis for the cell-grid kNN: the cell edge is about the expected K-NN radius of a surface-sampled
+    cloud (area ~ 4 pi: r = sqrt(4K/n) in units of the half extent).  Any G gives the same result; this one was the
+    fastest in the sweep of profiles/knn_cells_r2.md."""
+    g = int(round(2.0 / math.sqrt(4.0 * K / max(n, 1))))
+    return max(1, min(g, _lib.load().geoa3_cell_grid_max(n), 32))
+
+
+def cell_sort(pc, G, out=None):
+    """pc [b,3,n] -> per-cloud cell-grid blobs (uint8 [b, blob_bytes]) for `knn_cells` (geoa3_cell_sort)."""
+    require_cuda_f32(pc, "pc")
+    b, _, n = pc.shape
+    nb = _lib.load().geoa3_cell_blob_bytes(n, G)
+    blobs = out if out is not None else torch.empty(b, nb, device=pc.device, dtype=torch.uint8)
+    with _guard(pc):
+        _count(1)
+        check(_lib.load().geoa3_cell_sort(ptr(pc), b, n, G, ptr(blobs), stream(pc)))
+    return blobs
+
+
+def knn_cells(blobs, n, G, K, drop=0, return_dist=False, hint=None, out=None):
+    """Self-kNN member sets from the cell-grid blobs of `cell_sort`: idx [b,n,K-drop] i32 in ORIGINAL numbering (rows by
+    original query index, members in ascending cell-arrangement position), dist | None.  Exact for any hint / G."""
+    b = blobs.shape[0]
+    idx = out if out is not None else torch.empty(b, n, K - drop, device=blobs.device, dtype=torch.int32)
+    hk = 0
+    if hint is not None:
+        require_cuda_i32(hint, "hint")
+        hk = hint.shape[2]
+    dist = torch.empty(b, n, K - drop, device=blobs.device, dtype=torch.float32) if return_dist else None
+    with _guard(blobs):
+        _count(1)
+        check(_lib.load().geoa3_knn_cells(ptr(blobs), b, n, G, K, drop, ptr(hint), hk, ptr(idx), ptr(dist), stream(blobs)))
+    return idx, dist
+
+
+def nn_pair_cells(blobs_adv, blobs_ori, n, m, g_adv, g_ori, both=True, hint_a2o=None, hint_o2a=None, out=None):
+    """nn_pair over cell-grid blobs (geoa3_nn_pair_cells): -> d_a2o [b,n], jstar [b,n], d_o2a [b,m] | None, istar | None."""
+    b, dev = blobs_adv.shape[0], blobs_adv.device
+    if out is not None:
+        d1, j1, d2, i2 = out
+    else:
+        d1 = torch.empty(b, n, device=dev, dtype=torch.float32)
+        j1 = torch.empty(b, n, device=dev, dtype=torch.int32)
+        d2 = torch.empty(b, m, device=dev, dtype=torch.float32) if both else None
+        i2 = torch.empty(b, m, device=dev, dtype=torch.int32) if both else None
+    for h, nm in ((hint_a2o, "hint_a2o"), (hint_o2a, "hint_o2a")):
+        if h is not None:
+            require_cuda_i32(h, nm)
+    with _guard(blobs_adv):
+        _count(1)
+        check(_lib.load().geoa3_nn_pair_cells(ptr(blobs_adv), ptr(blobs_ori), b, n, m, g_adv, g_ori, ptr(hint_a2o),
+                                              ptr(hint_o2a), ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(blobs_adv)))
+    return d1, j1, d2, i2
 
 
 def kappa_loss_fwd(pc, normal=None, jstar=None, nbr=None, d_a2o=None, d_o2a=None, kappa_ori=None, m=None,

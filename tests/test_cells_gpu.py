@@ -1,0 +1,187 @@
+"""GPU parity (-m gpu) of the cell-grid searches — geoa3_cell_sort + geoa3_knn_cells / geoa3_nn_pair_cells — through the
+C ABI against the C oracle: bit-exact members / distances / argmins for every kind of hint, several grid sizes and the
+awkward clouds (lattice ties, duplicates, far-shifted, tiny, flat, single-valued, ragged, n != m, disjoint boxes), the
+blob layout itself, and the product path (HintBuffers with and without cells give the same losses and indices)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make(b, n, seed, std):
+    pc, nr, _ = synth.make_batch(b, n, seed)
+    return (pc + synth.make_offsets(b, n, seed=seed + 100, std=std)).astype(np.float32), pc, nr
+
+
+def knn_cases():
+    lat, _ = synth.lattice_cloud(343)
+    dup = make(2, 300, 4, 1e-2)[0]
+    dup[:, :, 150:200] = dup[:, :, 0:50]
+    flat = make(2, 400, 9, 1e-2)[0]
+    flat[:, 2, :] = 0.25
+    return [("smooth17", make(3, 1024, 2, 2e-2)[0], 17), ("smooth33", make(2, 1024, 1, 1e-2)[0], 33),
+            ("ragged9", make(2, 777, 5, 5e-2)[0], 9), ("lattice", np.stack([lat, lat * 0.5]), 9),
+            ("duplicates", np.ascontiguousarray(dup), 17), ("n2500", make(1, 2500, 3, 1e-2)[0], 17),
+            ("n40_K33", make(2, 40, 0, 1e-1)[0], 33), ("n20", make(2, 20, 0, 1e-1)[0], 17),
+            ("shifted", make(2, 500, 7, 1e-2)[0] + np.float32(100.0), 17),
+            ("tiny", make(2, 500, 8, 1e-2)[0] * np.float32(1e-3), 17), ("flat", flat, 17),
+            ("single_value", np.zeros((1, 3, 64), np.float32) + np.float32(0.5), 9),
+            ("K11_between_classes", make(2, 1024, 13, 1e-2)[0], 11), ("n4096_unstaged", make(1, 4096, 11, 1e-2)[0], 17)]
+
+
+@pytest.mark.parametrize("name,pts,K", knn_cases(), ids=[c[0] for c in knn_cases()])
+def test_knn_cells_members_exact(name, pts, K):
+    from geoa3_b200 import _lib, ops
+
+    rng = np.random.default_rng(5)
+    b, _, n = pts.shape
+    K = min(K, n)
+    P = cu(pts)
+    oi, od = O.knn(pts, pts, K)
+    want_i, want_d = oi[:, :, 1:], od[:, :, 1:]
+    exact = cu(want_i)
+    stale = cu(O.knn(pts + 0.05, pts[:, :, ::-1].copy(), K)[0][:, :, 1:])
+    junk = cu(rng.integers(-3, n + 50, (b, n, K - 1)).astype(np.int32))
+    zeros = torch.zeros(b, n, K - 1, dtype=torch.int32, device="cuda")
+    gmax = _lib.load().geoa3_cell_grid_max(n)
+    for G in sorted({1, 2, 5, ops.cell_grid_size(n, K), min(gmax, 13)}):
+        blobs = ops.cell_sort(P, G)
+        first = None
+        for h, tag in ((None, "none"), (exact, "exact"), (stale, "stale"), (junk, "junk"), (zeros, "dup")):
+            idx, dist = ops.knn_cells(blobs, n, G, K, drop=1, return_dist=True, hint=h)
+            i_, d_ = idx.cpu().numpy(), dist.cpu().numpy()
+            o = np.argsort(d_.view(np.int32).astype(np.int64) * 65536 + i_, -1)
+            assert np.array_equal(np.take_along_axis(i_, o, -1), want_i), (name, G, tag)
+            assert np.array_equal(np.take_along_axis(d_, o, -1), want_d), (name, G, tag)
+            first = idx if first is None else first
+            assert torch.equal(idx, first), (name, G, tag, "member order depends on the hint")
+    # drop = 0 keeps the self match; in place: the buffer is hint and output at once, three refreshes of a moving cloud
+    G = ops.cell_grid_size(n, K)
+    idx0 = ops.knn_cells(ops.cell_sort(P, G), n, G, K, drop=0)[0]
+    assert np.array_equal(np.sort(idx0.cpu().numpy(), -1), np.sort(oi, -1))
+    buf, cur = exact.clone(), pts
+    for step in range(3):
+        cur = (cur + synth.make_offsets(b, n, seed=40 + step, std=3e-3)).astype(np.float32)
+        ops.knn_cells(ops.cell_sort(cu(cur), G), n, G, K, drop=1, hint=buf, out=buf)
+        assert np.array_equal(np.sort(buf.cpu().numpy(), -1), np.sort(O.knn(cur, cur, K)[0][:, :, 1:], -1))
+
+
+def nn_cases():
+    lat, _ = synth.lattice_cloud(343)
+    d = list(make(2, 300, 4, 1e-2)[:2])
+    d[1] = d[1].copy()
+    d[1][:, :, 150:200] = d[1][:, :, 0:50]
+    return [("smooth", *make(3, 1024, 2, 2e-2)[:2]), ("ragged", *make(2, 1000, 1, 5e-2)[:2]),
+            ("n_ne_m", make(2, 333, 2, 1e-1)[0], make(2, 777, 6, 1e-2)[1]),
+            ("lattice_ties", np.stack([lat, lat * 0.5]), np.stack([lat * 0.5, lat])),
+            ("shifted", *[x + np.float32(100.0) for x in make(2, 500, 7, 1e-2)[:2]]),
+            ("tiny", *[x * np.float32(1e-3) for x in make(2, 500, 8, 1e-2)[:2]]),
+            ("disjoint_boxes", make(2, 400, 9, 1e-2)[0] + np.float32(3.0), make(2, 400, 9, 1e-2)[1]),
+            ("single_value_queries", np.zeros((1, 3, 64), np.float32) + np.float32(0.5), make(1, 90, 3, 1e-2)[1]),
+            ("duplicated_candidates", d[0], d[1]), ("n20", *make(2, 20, 0, 1e-1)[:2]), ("n4096", *make(1, 4096, 11, 1e-2)[:2])]
+
+
+@pytest.mark.parametrize("name,adv,ori", nn_cases(), ids=[c[0] for c in nn_cases()])
+def test_nn_pair_cells_bitexact(name, adv, ori):
+    from geoa3_b200 import _lib, ops
+
+    rng = np.random.default_rng(7)
+    adv, ori = np.ascontiguousarray(adv, np.float32), np.ascontiguousarray(ori, np.float32)
+    b, _, n = adv.shape
+    m = ori.shape[2]
+    od1, oj1 = O.nn1(adv, ori)
+    od2, oi2 = O.nn1(ori, adv)
+    A, Oc = cu(adv), cu(ori)
+    for ga, go in ((1, 1), (3, 5), (ops.cell_grid_size(n, 17), ops.cell_grid_size(m, 8)), (13, 11)):
+        ga = min(ga, _lib.load().geoa3_cell_grid_max(n))
+        go = min(go, _lib.load().geoa3_cell_grid_max(m))
+        ba, bo = ops.cell_sort(A, ga), ops.cell_sort(Oc, go)
+        hints = [(None, None, "none"), (cu(oj1), cu(oi2), "exact"),
+                 (cu(rng.integers(-3, m + 50, (b, n)).astype(np.int32)), cu(rng.integers(-3, n + 50, (b, m)).astype(np.int32)), "junk"),
+                 (torch.zeros(b, n, dtype=torch.int32, device="cuda"), torch.zeros(b, m, dtype=torch.int32, device="cuda"), "zeros")]
+        for h1, h2, tag in hints:
+            d1, j1, d2, i2 = ops.nn_pair_cells(ba, bo, n, m, ga, go, hint_a2o=h1, hint_o2a=h2)
+            assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2), (name, ga, go, tag)
+            assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2), (name, ga, go, tag)
+        d1, j1, d2, i2 = ops.nn_pair_cells(ba, bo, n, m, ga, go, both=False)
+        assert d2 is None and np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(d1.cpu().numpy(), od1)
+        # in place: hint and output are the same buffer
+        j, i = cu(oj1).clone(), cu(oi2).clone()
+        ops.nn_pair_cells(ba, bo, n, m, ga, go, hint_a2o=j, hint_o2a=i, out=(d1, j, torch.empty_like(i, dtype=torch.float32), i))
+        assert np.array_equal(j.cpu().numpy(), oj1) and np.array_equal(i.cpu().numpy(), oi2)
+
+
+def test_cell_blob_layout():
+    """The blob geoa3_cell_sort writes: a permutation of the cloud in cell-major order (ascending original index inside
+    a cell), start table consistent with the cell of every stored point, inverse permutation, and bitwise run-to-run
+    reproducibility (the sort hands out slots with shared atomics; the per-cell ordering pass makes it deterministic)."""
+    from geoa3_b200 import ops
+
+    pts = make(3, 1000, 2, 2e-2)[0]
+    n, G = 1000, 7
+    P = cu(pts)
+    blobs = ops.cell_sort(P, G)
+    assert blobs.shape[1] == ops._lib.load().geoa3_cell_blob_bytes(n, G) and blobs.shape[1] % 16 == 0
+    for _ in range(3):
+        assert torch.equal(ops.cell_sort(P, G), blobs)
+    raw = blobs.cpu().numpy()
+    nc = G ** 3
+    for c in range(pts.shape[0]):
+        gp = raw[c, :48].view(np.float32)
+        cl = raw[c, 64:64 + 16 * n].view(np.float32).reshape(n, 4)
+        orig = cl[:, 3].view(np.int32)
+        cs0 = 64 + 16 * n
+        cstart = raw[c, cs0:cs0 + 2 * (nc + 1)].view(np.uint16).astype(np.int64)
+        ip0 = cs0 + 2 * ((nc + 1 + 7) // 8 * 8)
+        ipos = raw[c, ip0:ip0 + 2 * n].view(np.uint16)
+        assert np.array_equal(np.sort(orig), np.arange(n))
+        assert np.array_equal(cl[:, :3], pts[c].T[orig])
+        assert np.array_equal(ipos[orig], np.arange(n))
+        assert cstart[0] == 0 and cstart[nc] == n and np.all(np.diff(cstart) >= 0)
+        lo, inv_h = gp[0:3], gp[3:6]
+        cell = np.clip(((cl[:, :3] - lo) * inv_h).astype(np.float32), 0, G - 1).astype(np.int64)
+        key = (cell[:, 2] * G + cell[:, 1]) * G + cell[:, 0]
+        assert np.all(np.diff(key) >= 0)
+        assert np.array_equal(np.searchsorted(key, np.arange(nc + 1), side="left"), cstart)
+        same = np.diff(key) == 0
+        assert np.all(np.diff(orig)[same] > 0)
+
+
+def test_hint_buffers_cells_equal_scan():
+    """The product path (fused loss through persistent HintBuffers) with the cell-grid searches and with the scanning
+    kernels: identical index buffers (as sets per row for the neighbour lists), loss values within rounding of the
+    summation order, over several steps of a moving cloud."""
+    from geoa3_b200 import loss_utils as L
+
+    b, n, k = 4, 1024, 16
+    adv0, ori, nrm = make(b, n, 3, 1e-2)
+    Oc, Nr = cu(ori), cu(nrm)
+    ko = L._get_kappa_ori(Oc, Nr, k)
+    hc, hs = L.HintBuffers(use_cells=True), L.HintBuffers(use_cells=False)
+    cur = adv0
+    for step in range(4):
+        cur = (cur + synth.make_offsets(b, n, seed=70 + step, std=4e-3)).astype(np.float32)
+        outs = []
+        for hb in (hc, hs):
+            L.clear_cache()
+            a = cu(cur).requires_grad_(True)
+            tot, cd, hd, cv = L.geo_loss(a, Oc, Nr, ko, k, 1.0, 0.1, 1.0, hints=hb)
+            tot.sum().backward()
+            outs.append((tot.detach(), cd, hd, cv, a.grad.clone()))
+        assert hc.cells_adv is not None and hs.cells_adv is None
+        assert torch.equal(hc.jstar, hs.jstar) and torch.equal(hc.istar, hs.istar)
+        assert torch.equal(hc.d1, hs.d1) and torch.equal(hc.d2, hs.d2)
+        assert torch.equal(hc.nbr[k].sort(-1)[0], hs.nbr[k].sort(-1)[0])
+        oi = O.knn(cur, cur, k + 1)[0][:, :, 1:]
+        assert np.array_equal(np.sort(hc.nbr[k].cpu().numpy(), -1), np.sort(oi, -1))
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])   # CD, HD: same inputs
+        for x, y in zip(outs[0], outs[1]):
+            assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max()) + 1e-12

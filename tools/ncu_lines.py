@@ -10,11 +10,14 @@ from collections import defaultdict
 
 rep, cubin, pat = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+import os
+ksel = ["-k", os.environ["NCU_K"]] if os.environ.get("NCU_K") else []   # NCU_K=regex:<name> picks one kernel of the report
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hdr]
-sass = [r for r in rows[hdr + 1:] if len(r) == len(h)]
+end = next((i for i in range(hdr + 1, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))  # first kernel only
+sass = [r for r in rows[hdr + 1:end] if len(r) == len(h)]
 dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
 lines, cur, infn = [], None, False
 for l in dis:
