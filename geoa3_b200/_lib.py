@@ -4,12 +4,13 @@ There is NO fallback: if the shared library is missing or a call fails, an excep
 torch is used only for device memory and the current stream.
 """
 import ctypes as C
+import os
 import os.path as osp
 
 import torch
 
 _HERE = osp.dirname(osp.abspath(__file__))
-SO_PATH = osp.join(_HERE, "libgeoa3_b200.so")
+SO_PATH = os.environ.get("GEOA3_SO_PATH") or osp.join(_HERE, "libgeoa3_b200.so")  # override: A/B builds (tools only)
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -22,7 +23,7 @@ SIGNATURES = {
     "geoa3_knn_set": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "geoa3_cell_grid_max": (_i, [_i]),
     "geoa3_cell_blob_bytes": (_sz, [_i, _i]),
-    "geoa3_cell_sort": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "geoa3_cell_sort": (_i, [_vp, _i, _i, _i, _f, _i, _i, _i, _vp, _vp]),
     "geoa3_knn_cells": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "geoa3_nn_pair_cells": (_i, [_vp, _vp, _i, _i, _i, _i, _i] + [_vp] * 7),
     "geoa3_group_bbox_floats": (_sz, [_i]),

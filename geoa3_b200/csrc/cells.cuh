@@ -6,7 +6,7 @@
 
 namespace geoa3 {
 
-constexpr int KC_GP = 12;            // grid parameters per cloud: lo xyz, inv_h xyz, h xyz, slack, G-1, pad
+constexpr int KC_GP = 16;            // grid parameters per cloud: lo xyz, inv_h xyz, h xyz, slack, (cells per axis - 1) xyz, cells per axis xyz
 constexpr float KC_INF = __builtin_huge_valf();
 constexpr float KC_REL = 1.00001f;
 
@@ -33,6 +33,17 @@ __device__ __forceinline__ unsigned kc_lds16(unsigned a) {
   unsigned short v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
   return v;
+}
+__device__ __forceinline__ unsigned kc_lds32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void kc_sts32(unsigned a, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void kc_sts16(unsigned a, unsigned v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
 __device__ __forceinline__ void kc_sts64(unsigned a, float d, int i) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(__float_as_uint(d)), "r"(i) : "memory");

@@ -32,25 +32,41 @@
 #define KC_EXTRA 11
 #endif
 #ifndef KC_THREADS
-#define KC_THREADS 128
+#define KC_THREADS 512
+#endif
+#ifndef KC_HSCALE
+#define KC_HSCALE 1.0f   // cell edge / estimated radius of a kref-point ball (speed only)
+#endif
+#ifndef KC_ROWS
+#define KC_ROWS 24   // row-table slots per query (fast path); a query with more non-empty rows takes the careful path
 #endif
 
 namespace geoa3 {
 
 constexpr int KC_SORT_THREADS = 1024;
 
-__host__ __device__ inline size_t kc_sort_smem(int n, int nc) {
-  return (size_t)n * 4 + (size_t)(nc + 1) * 4 + (size_t)nc * 4 + (size_t)((n + 1) & ~1) * 2 + 32 * 4 + 32 * 8 * 4 + KC_GP * 4;
+constexpr int KC_PROBE = 16;  // probe grid (cells per axis) of the surface-density estimate
+
+__host__ __device__ inline size_t kc_sort_smem(int n, int ncap) {
+  const int nct = ncap > KC_PROBE * KC_PROBE * KC_PROBE ? ncap : KC_PROBE * KC_PROBE * KC_PROBE;
+  return (size_t)n * 4 + (size_t)(ncap + 1) * 4 + (size_t)nct * 4 + (size_t)((n + 1) & ~1) * 2 + 32 * 4 + 32 * 8 * 4 + KC_GP * 4;
 }
 
+// ncap: capacity of the cell table (the blob layout depends on it, not on the grid actually used).
+// fx, fy, fz > 0: that grid, cubic cells of edge (longest side / largest f).  Otherwise the grid is chosen per cloud:
+// cubic cells whose edge is about the radius of a ball holding `kref` points, estimated from the cloud's surface
+// density (occupied cells of a 16^3 probe grid ~ surface area), as many cells per axis as the box needs, the edge
+// grown until the grid fits ncap.  The choice only affects speed.
 __global__ void __launch_bounds__(KC_SORT_THREADS)
-cell_sort_kernel(const float* __restrict__ pc, int n, int G, unsigned char* __restrict__ blobs) {
+cell_sort_kernel(const float* __restrict__ pc, int n, int ncap, float kref, int fx, int fy, int fz,
+                 unsigned char* __restrict__ blobs) {
   extern __shared__ __align__(16) unsigned char kc_smem[];
-  const int nc = G * G * G;
+  const int nc = ncap;
+  const int nct = ncap > KC_PROBE * KC_PROBE * KC_PROBE ? ncap : KC_PROBE * KC_PROBE * KC_PROBE;
   int* keys = reinterpret_cast<int*>(kc_smem);      // [n]
   int* offs = keys + n;                             // [nc + 1]
-  int* cnt = offs + nc + 1;                         // [nc]
-  int* scan = cnt + nc;                             // [32]
+  int* cnt = offs + nc + 1;                         // [max(nc, probe cells)]
+  int* scan = cnt + nct;                            // [32]
   float* red = reinterpret_cast<float*>(scan + 32); // [32][8]
   float* gp = red + 32 * 8;                         // [KC_GP]
   uint16_t* ent = reinterpret_cast<uint16_t*>(gp + KC_GP);  // [n]
@@ -86,38 +102,129 @@ cell_sort_kernel(const float* __restrict__ pc, int n, int G, unsigned char* __re
       lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, s)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, s));
     }
     if (lane == 0) {
-      const float lo[3] = {lx, ly, lz}, hi[3] = {hx, hy, hz};
-      float ma = 0.f;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const float ext = hi[a] - lo[a];
-        const bool ok = ext > 0.f && ext < 3e38f;  // empty / single-valued / non-finite axis: one cell layer
-        gp[a] = ok ? lo[a] : (lo[a] < 3e38f ? lo[a] : 0.f);
-        gp[3 + a] = ok ? (float)G / ext : 0.f;
-        gp[6 + a] = ok ? ext / (float)G : 0.f;
-        ma = fmaxf(ma, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
-      }
-      gp[9] = ma < 3e38f ? 8e-6f * ma + 1e-30f : 0.f;
-      gp[10] = (float)(G - 1);
-      gp[11] = 0.f;
+      red[0] = lx; red[1] = ly; red[2] = lz; red[3] = hx; red[4] = hy; red[5] = hz;
     }
   }
   __syncthreads();
-  if (tid < KC_HDR / 4) reinterpret_cast<float*>(blob)[tid] = tid < KC_GP ? gp[tid] : 0.f;
-  const float gm1 = gp[10];
-  for (int i = tid; i < n; i += KC_SORT_THREADS) {
-    const int cx = kc_cell(p[i], gp[0], gp[3], gm1), cy = kc_cell(p[n + i], gp[1], gp[4], gm1),
-              cz = kc_cell(p[2 * n + i], gp[2], gp[5], gm1);
-    keys[i] = (cz * G + cy) * G + cx;
+  const float blo[3] = {red[0], red[1], red[2]}, bhi[3] = {red[3], red[4], red[5]};
+  float ext[3], emax = 0.f, ma = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float e = bhi[a] - blo[a];
+    ext[a] = (e > 0.f && e < 3e38f) ? e : 0.f;  // empty / single-valued / non-finite axis: one cell layer
+    emax = fmaxf(emax, ext[a]);
+    ma = fmaxf(ma, fmaxf(fabsf(blo[a]), fabsf(bhi[a])));
+  }
+  int nocc = 0;
+  if (fx <= 0 && emax > 0.f) {  // surface-density probe: how many cells of a 16^3 grid over the box hold points
+    const float ip = (float)KC_PROBE / emax, pm1 = (float)(KC_PROBE - 1);
+    for (int c = tid; c < KC_PROBE * KC_PROBE * KC_PROBE; c += KC_SORT_THREADS) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += KC_SORT_THREADS) {
+      const int cx = kc_cell(p[i], blo[0], ip, pm1), cy = kc_cell(p[n + i], blo[1], ip, pm1), cz = kc_cell(p[2 * n + i], blo[2], ip, pm1);
+      cnt[(cz * KC_PROBE + cy) * KC_PROBE + cx] = 1;
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int c = tid; c < KC_PROBE * KC_PROBE * KC_PROBE; c += KC_SORT_THREADS) mine += cnt[c];
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) scan[w] = mine;
+    __syncthreads();
+    for (int i = 0; i < KC_SORT_THREADS / 32; ++i) nocc += scan[i];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int g[3];
+    float h;
+    if (fx > 0) {
+      const int fs[3] = {fx, fy, fz};
+      h = emax / (float)max(fx, max(fy, fz));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) g[a] = fs[a];
+    } else {
+      // area ~ nocc * (emax/16)^2, density = n / area, a ball of radius r on the surface holds kref points
+      const float hp = emax / (float)KC_PROBE;
+      h = sqrtf(kref * (float)max(nocc, 1) * hp * hp / (3.14159265f * (float)n)) * KC_HSCALE;
+      h = fmaxf(h, emax / 64.f);
+      for (int it = 0; it < 64; ++it) {
+        long long tot = 1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          g[a] = h > 0.f ? min(64, max(1, (int)ceilf(ext[a] / h))) : 1;
+          tot *= g[a];
+        }
+        if (tot <= ncap) break;
+        h *= 1.1f;
+      }
+      if ((long long)g[0] * g[1] * g[2] > ncap) { g[0] = g[1] = g[2] = 1; h = emax; }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const bool ok = ext[a] > 0.f && h > 0.f;
+      gp[a] = blo[a] < 3e38f ? blo[a] : 0.f;
+      gp[3 + a] = ok ? 1.f / h : 0.f;
+      gp[6 + a] = ok ? h : 0.f;
+      gp[10 + a] = (float)(g[a] - 1);
+    }
+    gp[9] = ma < 3e38f ? 8e-6f * ma + 1e-30f : 0.f;
+    gp[13] = (float)g[0];
+    gp[14] = (float)g[1];
+    gp[15] = (float)g[2];
   }
   __syncthreads();
-  build_csr_sorted<KC_SORT_THREADS, uint16_t>(keys, n, nc, 0u, offs, cnt, ent, scan);
+  if (tid < KC_HDR / 4) reinterpret_cast<float*>(blob)[tid] = tid < KC_GP ? gp[tid] : 0.f;
+  const int gx = (int)gp[13], gy = (int)gp[14];
+  for (int i = tid; i < n; i += KC_SORT_THREADS) {
+    const int cx = kc_cell(p[i], gp[0], gp[3], gp[10]), cy = kc_cell(p[n + i], gp[1], gp[4], gp[11]),
+              cz = kc_cell(p[2 * n + i], gp[2], gp[5], gp[12]);
+    keys[i] = (cz * gy + cy) * gx + cx;
+  }
+  __syncthreads();
+  for (int c = tid; c < nc; c += KC_SORT_THREADS) cnt[c] = 0;
+  __syncthreads();
+  // counting sort by cell.  Slots inside a cell are handed out by shared atomics in arbitrary order; the order is then
+  // made canonical (ascending original index) by RANKING: every point counts the smaller indices of its own cell
+  // segment and goes to segment start + rank.  All points of a cell rank in parallel, so a crowded cell costs its
+  // length in steps, not its length squared (a single-thread insertion sort took 200 us on flat clouds).
+  for (int i = tid; i < n; i += KC_SORT_THREADS) atomicAdd(&cnt[keys[i]], 1);
+  __syncthreads();
+  {
+    const int per = (nc + KC_SORT_THREADS - 1) / KC_SORT_THREADS;
+    const int c_beg = min(nc, tid * per), c_end = min(nc, c_beg + per);
+    int local = 0;
+    for (int c = c_beg; c < c_end; ++c) local += cnt[c];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) scan[w] = incl;
+    __syncthreads();
+    int run = incl - local;
+    for (int i = 0; i < w; ++i) run += scan[i];
+    for (int c = c_beg; c < c_end; ++c) {
+      const int k = cnt[c];
+      offs[c] = run;
+      cnt[c] = run;  // becomes the fill cursor
+      run += k;
+    }
+    if (tid == KC_SORT_THREADS - 1) offs[nc] = n;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += KC_SORT_THREADS) ent[atomicAdd(&cnt[keys[i]], 1)] = (uint16_t)i;
+  __syncthreads();
   float4* o4 = reinterpret_cast<float4*>(blob + KC_HDR);
   uint16_t* ip = reinterpret_cast<uint16_t*>(blob + kc_ip_off(n, nc));
   for (int t = tid; t < n; t += KC_SORT_THREADS) {
     const int o = ent[t];
-    o4[t] = make_float4(p[o], p[n + o], p[2 * n + o], __int_as_float(o));
-    ip[o] = (uint16_t)t;
+    const int c = keys[o];
+    const int b0 = offs[c], e0 = offs[c + 1];
+    int rank = 0;
+    for (int u = b0; u < e0; ++u) rank += (int)ent[u] < o;
+    const int pos = b0 + rank;
+    o4[pos] = make_float4(p[o], p[n + o], p[2 * n + o], __int_as_float(o));
+    ip[o] = (uint16_t)pos;
   }
   uint16_t* cs = reinterpret_cast<uint16_t*>(blob + kc_cs_off(n));
   for (int c = tid; c < ((nc + 1 + 7) & ~7); c += KC_SORT_THREADS) cs[c] = (uint16_t)offs[min(c, nc)];
@@ -127,44 +234,46 @@ cell_sort_kernel(const float* __restrict__ pc, int n, int G, unsigned char* __re
 template <int K>
 struct KcCfg {
   static constexpr int R = K + KC_EXTRA;  // list slots per query
-  static constexpr int T = KC_THREADS;    // one query per thread
+  static constexpr int T = K <= 17 ? KC_THREADS : (KC_THREADS > 256 ? 256 : KC_THREADS);  // one query per thread
+  static constexpr int W = (KC_ROWS + 1) > R ? (KC_ROWS + 1) : R;  // words of per-query scratch (row table, then distances)
 };
 
-// list entry = (pinned distance bits, ORIGINAL index); dead entries carry a negative distance
-__host__ __device__ inline size_t kc_list_bytes(int r, int t) { return (size_t)r * t * 8; }
+// Per-query shared memory: list of ORIGINAL indices (uint16 [R][T]) + a scratch column of 32-bit words [W][T] that
+// holds the query's row table while it scans and the members' pinned distances afterwards (dead entries: negative).
+__host__ __device__ inline size_t kc_list_bytes(int r, int w, int t) { return ((size_t)r * t * 2 + (size_t)w * t * 4 + 15) & ~(size_t)15; }
 
 // Marks the `rm` largest (distance, original index) keys of a query's list dead (d = -2).  Per thread, loop form:
-// it runs under divergence.  l_: the thread's column (stride COLS).
+// it runs under divergence.  d_ / v_: the thread's columns (stride COLS).
 template <int COLS>
-__device__ __forceinline__ void kc_mark(uint2* __restrict__ l_, int cnt, int rm) {
+__device__ __forceinline__ void kc_mark(float* __restrict__ d_, const uint16_t* __restrict__ v_, int cnt, int rm) {
   for (; rm > 0; --rm) {
     float md = -1.f;
     int bs = 0;
     unsigned bi = 0u;
     for (int s = 0; s < cnt; ++s) {
-      const uint2 e = l_[s * COLS];
-      const float d = __uint_as_float(e.x);
+      const float d = d_[s * COLS];
       if (d >= md) {
-        if (d > md || e.y > bi) { md = d; bs = s; bi = e.y; }
+        const unsigned vi = v_[s * COLS];
+        if (d > md || vi > bi) { md = d; bs = s; bi = vi; }
       }
     }
-    l_[bs * COLS].x = __float_as_uint(-2.f);
+    d_[bs * COLS] = -2.f;
   }
 }
 
 // List overflow (careful path only): keeps the kk smallest keys in arrival order, returns the new length and lowers
 // *tau to the largest kept distance.
 template <int COLS>
-__device__ __forceinline__ int kc_cut(uint2* __restrict__ l_, int cnt, int kk, float* tau) {
+__device__ __forceinline__ int kc_cut(float* __restrict__ d_, uint16_t* __restrict__ v_, int cnt, int kk, float* tau) {
   if (cnt <= kk) return cnt;
-  kc_mark<COLS>(l_, cnt, cnt - kk);
+  kc_mark<COLS>(d_, v_, cnt, cnt - kk);
   int w = 0;
   float mx = 0.f;
   for (int s = 0; s < cnt; ++s) {  // close the gaps
-    const uint2 e = l_[s * COLS];
-    const float d = __uint_as_float(e.x);
+    const float d = d_[s * COLS];
     if (d >= 0.f) {
-      l_[w * COLS] = e;
+      d_[w * COLS] = d;
+      v_[w * COLS] = v_[s * COLS];
       mx = fmaxf(mx, d);
       ++w;
     }
@@ -175,36 +284,38 @@ __device__ __forceinline__ int kc_cut(uint2* __restrict__ l_, int cnt, int kk, f
 
 // Writes the live entries of a list (arrival order = ascending position in the cell arrangement).
 template <int COLS>
-__device__ __forceinline__ void kc_write(const uint2* __restrict__ l_, int cnt, int kout, int32_t* __restrict__ io,
-                                         float* __restrict__ dn) {
+__device__ __forceinline__ void kc_write(const float* __restrict__ d_, const uint16_t* __restrict__ v_, int cnt, int kout,
+                                         int32_t* __restrict__ io, float* __restrict__ dn) {
   int o = 0;
   for (int s = 0; s < cnt && o < kout; ++s) {
-    const uint2 e = l_[s * COLS];
-    if (__uint_as_float(e.x) >= 0.f) {
-      io[o] = (int32_t)e.y;
-      if (dn) dn[o] = __uint_as_float(e.x);
+    const float d = d_[s * COLS];
+    if (d >= 0.f) {
+      io[o] = (int32_t)v_[s * COLS];
+      if (dn) dn[o] = d;
       ++o;
     }
   }
 }
 
 template <int K, int T, bool STAGED>
-__global__ void __launch_bounds__(T)
-knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout, int drop, const int32_t* hint, int hint_k,
-                 int32_t* idx_out, float* __restrict__ dist_out, int kk) {
+__global__ void __launch_bounds__(T, 1024 / T)
+knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int ncap, int kout, int drop,
+                 const int32_t* hint, int hint_k, int32_t* idx_out, float* __restrict__ dist_out, int kk) {
   // kk = min(requested K, n): the list target (the template K is the capacity class)
   constexpr int R = KcCfg<K>::R;
+  constexpr int WS = KcCfg<K>::W;
   constexpr int HV = (K - 1) % 4 == 0 ? (K - 1) / 4 : 0;  // hint row as int4 registers when hint_k == K-1
   extern __shared__ __align__(16) unsigned char kc_smem[];
-  const int nc = G * G * G;
+  const int nc = ncap;
   const int cloud = blockIdx.y, tid = threadIdx.x;
   const size_t blob_bytes = kc_blob_bytes(n, nc);
   const unsigned char* gblob = blobs + (size_t)cloud * blob_bytes;
-  uint2* l_ = reinterpret_cast<uint2*>(kc_smem) + tid;  // this query's list: column tid of [R][T]
+  float* d_ = reinterpret_cast<float*>(kc_smem) + tid;                               // scratch column of [WS][T]
+  uint16_t* v_ = reinterpret_cast<uint16_t*>(kc_smem + (size_t)WS * T * 4) + tid;   // list column of [R][T]
   const unsigned char* blob = gblob;
   __shared__ __align__(8) unsigned long long kc_bar;
   if (STAGED) {  // the whole blob is one contiguous, 16-byte sized block: a single TMA bulk copy stages it
-    unsigned char* sblob = kc_smem + kc_list_bytes(R, T);
+    unsigned char* sblob = kc_smem + kc_list_bytes(R, WS, T);
     kc_stage_issue(&kc_bar, sblob, gblob, (unsigned)blob_bytes);
     blob = sblob;
   }
@@ -226,7 +337,8 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
   const uint16_t* scs = reinterpret_cast<const uint16_t*>(blob + kc_cs_off(n));
   const uint16_t* sip = reinterpret_cast<const uint16_t*>(blob + kc_ip_off(n, nc));
   const float lox = sgp[0], loy = sgp[1], loz = sgp[2], ihx = sgp[3], ihy = sgp[4], ihz = sgp[5];
-  const float slack = sgp[9], gm1 = sgp[10];
+  const float slack = sgp[9], gmx = sgp[10], gmy = sgp[11], gmz = sgp[12];
+  const int gx = (int)sgp[13], gy = (int)sgp[14];  // this cloud's grid (cells per axis)
 
   float tau = KC_INF;
   if (hint != nullptr && hint_k + 1 >= kk && live) {
@@ -252,10 +364,14 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
   int32_t* io = idx_out + ((size_t)cloud * n + qo) * kout;
   float* dn = dist_out ? dist_out + ((size_t)cloud * n + qo) * kout : nullptr;
 
-  // ---- fast path (hinted queries, staged blob): every lane walks ITS OWN rows (row offsets relative to the lane's
-  // first row are warp-uniform), appends are branch-free, the query itself is skipped (drop == 1: it is the smallest
-  // key unless a second point sits at distance 0).  A list overflow, a zero-distance duplicate or a bound that turns
-  // out invalid (fewer than K survivors) sends the query to the careful path below.
+  // ---- fast path (hinted queries, staged blob).  Phase 1: the lane's non-empty cell rows within reach of tau go into
+  // its row table (row offsets relative to the lane's first row are warp-uniform; the x interval per row comes from
+  // what the row's y/z slab distance leaves of tau).  Phase 2: every lane walks ITS OWN candidate stream — the warp
+  // runs as long as its longest stream, not as long as the sum of the longest rows — with branch-free appends of the
+  // ORIGINAL index; the query itself is skipped (drop == 1: it is the smallest key unless a second point sits at
+  // distance 0).  Phase 3: the members' pinned distances are recomputed into the (now free) row-table column, the
+  // largest keys beyond K are marked and the rest is written.  A list or row-table overflow, a zero-distance duplicate
+  // or a bound that turns out invalid (fewer than K survivors) sends the query to the careful path below.
   bool careful = live;
   const bool fa = STAGED && live && tau < KC_INF && drop <= 1;
   if (STAGED && __any_sync(0xffffffffu, fa)) {
@@ -263,66 +379,91 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
     int z0 = 0, y0 = 0, nz = -1, ny = -1;
     if (fa) {
       const float r = kc_sqrt(tau * KC_REL) * KC_REL + slack;
-      z0 = kc_cell(q.z - r, loz, ihz, gm1);
-      nz = kc_cell(q.z + r, loz, ihz, gm1) - z0;
-      y0 = kc_cell(q.y - r, loy, ihy, gm1);
-      ny = kc_cell(q.y + r, loy, ihy, gm1) - y0;
+      z0 = kc_cell(q.z - r, loz, ihz, gmz);
+      nz = kc_cell(q.z + r, loz, ihz, gmz) - z0;
+      y0 = kc_cell(q.y - r, loy, ihy, gmy);
+      ny = kc_cell(q.y + r, loy, ihy, gmy) - y0;
     }
     const int wz = __reduce_max_sync(0xffffffffu, nz), wy = __reduce_max_sync(0xffffffffu, ny);
     const float r2 = fmaf(tau, KC_REL, 1e-37f);
     const float hy = sgp[7], hz = sgp[8];
     const unsigned a4 = (unsigned)__cvta_generic_to_shared(s4);
     const unsigned acs = (unsigned)__cvta_generic_to_shared(scs);
-    const unsigned l0 = (unsigned)__cvta_generic_to_shared(l_);
-    const unsigned lend = l0 + R * T * 8;
-    unsigned lp = l0;  // next free list slot (keeps advancing past the end: that is how an overflow is seen)
+    const unsigned aip = (unsigned)__cvta_generic_to_shared(sip);
+    const unsigned l0 = (unsigned)__cvta_generic_to_shared(v_);
+    const unsigned lend = l0 + R * T * 2;
+    const unsigned t0 = (unsigned)__cvta_generic_to_shared(d_);
+    unsigned tp = t0;
+    int tot = 0, nrow = 0;
+    bool bad = false;
     for (int oz = 0; oz <= wz; ++oz) {
       const int rz = z0 + min(oz, max(nz, 0));
       const float zl = fmaf((float)rz, hz, loz);
-      const float ez = fmaxf(fmaxf(zl - q.z, q.z - (zl + hz)) - slack, 0.f);  // lower bound of |c.z - q.z| in this slab
+      const float ez = fmaxf(fmaxf(zl - q.z, q.z - ((float)rz >= gmz ? KC_INF : zl + hz)) - slack, 0.f);  // lower bound of |c.z - q.z| in this slab
       const float remz = oz <= nz ? r2 - ez * ez : -1.f;
       for (int oy = 0; oy <= wy; ++oy) {
         const int ry = y0 + min(oy, max(ny, 0));
         const float yl = fmaf((float)ry, hy, loy);
-        const float ey = fmaxf(fmaxf(yl - q.y, q.y - (yl + hy)) - slack, 0.f);
+        const float ey = fmaxf(fmaxf(yl - q.y, q.y - ((float)ry >= gmy ? KC_INF : yl + hy)) - slack, 0.f);
         const float rem = oy <= ny ? remz - ey * ey : -1.f;  // what is left for (c.x - q.x)^2
         const float rx = kc_sqrt(fmaxf(rem, 0.f)) * KC_REL + slack;
-        const unsigned ab = acs + (unsigned)((rz * G + ry) * G) * 2u;
-        const int x0 = kc_cell(q.x - rx, lox, ihx, gm1), x1 = kc_cell(q.x + rx, lox, ihx, gm1);
+        const unsigned ab = acs + (unsigned)((rz * gy + ry) * gx) * 2u;
+        const int x0 = kc_cell(q.x - rx, lox, ihx, gmx), x1 = kc_cell(q.x + rx, lox, ihx, gmx);
         const int s = (int)kc_lds16(ab + x0 * 2);
         const int len = rem >= 0.f ? (int)kc_lds16(ab + x1 * 2 + 2) - s : 0;
-        const int wl = __reduce_max_sync(0xffffffffu, len);
-        const unsigned ca = a4 + (unsigned)s * 16u;
-        const unsigned cl = ca + (unsigned)max(len - 1, 0) * 16u;  // reads past the lane's own range are clamped to it
-        auto eval = [&](int i, const float4 c) {
-          const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);  // the pinned arithmetic decides
-          const int ci = __float_as_int(c.w);
-          const bool pass = i < len && d <= tau && ci != qskip;
-          if (pass && lp < lend) kc_sts64(lp, d, ci);
-          if (pass) lp += T * 8;
-        };
-        int i = 0;
-        for (; i + 1 < wl; i += 2) {
-          const float4 c0 = kc_lds128(min(ca + (unsigned)i * 16u, cl));
-          const float4 c1 = kc_lds128(min(ca + (unsigned)i * 16u + 16u, cl));
-          eval(i, c0);
-          eval(i + 1, c1);
+        if (len > 0) {
+          if (nrow < KC_ROWS) kc_sts32(tp, (unsigned)s | ((unsigned)len << 16));
+          else bad = true;
+          tp += T * 4;
+          ++nrow;
+          tot += len;
         }
-        if (i < wl) eval(i, kc_lds128(min(ca + (unsigned)i * 16u, cl)));
+      }
+    }
+    kc_sts32(t0 + min(nrow, KC_ROWS) * (T * 4), 0xffff0000u);  // sentinel: a finished lane idles on it
+    const int wtot = __reduce_max_sync(0xffffffffu, bad ? 0 : tot);
+    if (bad) tot = 0;
+    unsigned lp = l0;  // next free list slot (keeps advancing past the end: that is how an overflow is seen)
+    {
+      const unsigned aend = a4 + (unsigned)(n - 1) * 16u;
+      unsigned ca = a4;
+      int left = 0;
+      tp = t0;
+#pragma unroll 2
+      for (int it = 0; it < wtot; ++it) {
+        if (left == 0) {
+          const unsigned e = kc_lds32(tp);
+          tp += T * 4;
+          ca = a4 + (e & 0xffffu) * 16u;
+          left = (int)(e >> 16);
+        }
+        const float4 c = kc_lds128(min(ca, aend));
+        ca += 16u;
+        --left;
+        const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);  // the pinned arithmetic decides
+        const int ci = __float_as_int(c.w);
+        const bool pass = it < tot && d <= tau && ci != qskip;
+        if (pass && lp < lend) kc_sts16(lp, (unsigned)ci);
+        if (pass) lp += T * 2;
       }
     }
     if (fa) {
-      const int cnt = (int)(lp - l0) / (T * 8);
+      const int cnt = (int)(lp - l0) / (T * 2);
       const int kt = kk - (drop == 1 ? 1 : 0);
-      bool good = cnt >= kt && cnt <= R;
-      if (good && drop == 1) {  // a zero-distance neighbour competes with the query for being the dropped key
+      bool good = !bad && cnt >= kt && cnt <= R;
+      if (good) {  // the members' distances, into the scratch column (the row table is no longer needed)
         float dm = KC_INF;
-        for (int s2 = 0; s2 < cnt; ++s2) dm = fminf(dm, __uint_as_float(l_[s2 * T].x));
-        good = dm > 0.f;
+        for (int s2 = 0; s2 < cnt; ++s2) {
+          const float4 c = kc_lds128(a4 + kc_lds16(aip + (unsigned)v_[s2 * T] * 2u) * 16u);
+          const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);
+          d_[s2 * T] = d;
+          dm = fminf(dm, d);
+        }
+        good = drop != 1 || dm > 0.f;  // a zero-distance neighbour competes with the query for being the dropped key
       }
       if (good) {
-        kc_mark<T>(l_, cnt, cnt - kt);
-        kc_write<T>(l_, cnt, kout, io, dn);
+        kc_mark<T>(d_, v_, cnt, cnt - kt);
+        kc_write<T>(d_, v_, cnt, kout, io, dn);
         careful = false;
       }
     }
@@ -339,27 +480,27 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
     int z0, z1, y0, y1;
     {
       const float r = sqrtf(tau * KC_REL) * KC_REL + slack;
-      z0 = act ? kc_cell(q.z - r, loz, ihz, gm1) : INT_MAX;
-      z1 = act ? kc_cell(q.z + r, loz, ihz, gm1) : -1;
-      y0 = act ? kc_cell(q.y - r, loy, ihy, gm1) : INT_MAX;
-      y1 = act ? kc_cell(q.y + r, loy, ihy, gm1) : -1;
+      z0 = act ? kc_cell(q.z - r, loz, ihz, gmz) : INT_MAX;
+      z1 = act ? kc_cell(q.z + r, loz, ihz, gmz) : -1;
+      y0 = act ? kc_cell(q.y - r, loy, ihy, gmy) : INT_MAX;
+      y1 = act ? kc_cell(q.y + r, loy, ihy, gmy) : -1;
       z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
       y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
     }
     for (int rz = z0; rz <= z1; ++rz) {
       const float hz = sgp[8];
       const float zl = fmaf((float)rz, hz, loz);
-      const float ez = fmaxf(fmaxf(zl - q.z, q.z - (zl + hz)) - slack, 0.f);
+      const float ez = fmaxf(fmaxf(zl - q.z, q.z - ((float)rz >= gmz ? KC_INF : zl + hz)) - slack, 0.f);
       const float ez2 = ez * ez;
       for (int ry = y0; ry <= y1; ++ry) {
         const float hy = sgp[7];
         const float yl = fmaf((float)ry, hy, loy);
-        const float ey = fmaxf(fmaxf(yl - q.y, q.y - (yl + hy)) - slack, 0.f);
+        const float ey = fmaxf(fmaxf(yl - q.y, q.y - ((float)ry >= gmy ? KC_INF : yl + hy)) - slack, 0.f);
         const float rem = fmaf(tau, KC_REL, 1e-37f) - ez2 - ey * ey;
         const bool ok = act && rem >= 0.f;
         const float rx = sqrtf(fmaxf(rem, 0.f)) * KC_REL + slack;
-        const int base = (rz * G + ry) * G;
-        const int x0 = kc_cell(q.x - rx, lox, ihx, gm1), x1 = kc_cell(q.x + rx, lox, ihx, gm1);
+        const int base = (rz * gy + ry) * gx;
+        const int x0 = kc_cell(q.x - rx, lox, ihx, gmx), x1 = kc_cell(q.x + rx, lox, ihx, gmx);
         const int s = scs[base + x0];
         const int len = ok ? (int)scs[base + x1 + 1] - s : 0;
         const int wl = __reduce_max_sync(0xffffffffu, len);
@@ -370,8 +511,9 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
             const float4 c = cp[i];
             const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);
             if (d <= tau) {
-              if (cnt == R) cnt = kc_cut<T>(l_, cnt, kk, &tau);  // makes room and tightens tau
-              l_[cnt * T] = make_uint2(__float_as_uint(d), (unsigned)__float_as_int(c.w));
+              if (cnt == R) cnt = kc_cut<T>(d_, v_, cnt, kk, &tau);  // makes room and tightens tau
+              d_[cnt * T] = d;
+              v_[cnt * T] = (uint16_t)__float_as_int(c.w);
               ++cnt;
             }
           }
@@ -382,21 +524,21 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
     const bool fail = act && cnt < kk;
     rescan = __any_sync(0xffffffffu, fail);
     if (act && !fail) {
-      kc_mark<T>(l_, cnt, cnt - kk);
+      kc_mark<T>(d_, v_, cnt, cnt - kk);
       for (int t = 0; t < drop; ++t) {  // the `drop` smallest (distance, original index) keys are no members
         float md = KC_INF;
         int bs = 0;
         unsigned bo = 0xffffffffu;
         for (int s2 = 0; s2 < cnt; ++s2) {
-          const uint2 e = l_[s2 * T];
-          const float d = __uint_as_float(e.x);
+          const float d = d_[s2 * T];
           if (d >= 0.f && d <= md) {
-            if (d < md || e.y < bo) { md = d; bs = s2; bo = e.y; }
+            const unsigned vi = v_[s2 * T];
+            if (d < md || vi < bo) { md = d; bs = s2; bo = vi; }
           }
         }
-        l_[bs * T].x = __float_as_uint(-1.f);
+        d_[bs * T] = -1.f;
       }
-      kc_write<T>(l_, cnt, kout, io, dn);
+      kc_write<T>(d_, v_, cnt, kout, io, dn);
       act = false;
     }
     if (fail) { tau = KC_INF; cnt = 0; }
@@ -404,25 +546,31 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int G, int kout
 }
 
 template <int K>
-static int launch_knn_cells_k(const unsigned char* blobs, int b, int n, int G, int kreq, int kout, int drop,
+static int launch_knn_cells_k(const unsigned char* blobs, int b, int n, int ncap, int kreq, int kout, int drop,
                               const int32_t* hint, int hint_k, int32_t* idx, float* dist, cudaStream_t s) {
   constexpr int T = KcCfg<K>::T;
   constexpr int R = KcCfg<K>::R;
-  const int nc = G * G * G;
-  const size_t list = kc_list_bytes(R, T), stage = kc_blob_bytes(n, nc);
-  const bool staged = list + stage <= 100 * 1024;  // otherwise the arrangement is read through L1 / L2
+  const int nc = ncap;
+  const size_t list = kc_list_bytes(R, KcCfg<K>::W, T), stage = kc_blob_bytes(n, nc);
+  const bool staged = list + stage <= 226 * 1024;  // otherwise the arrangement is read through L1 / L2 (careful path only)
   dim3 grid(ceil_div(n, T), b, 1);
   cudaError_t e = cudaSuccess;
   if (staged) {
     static PerDeviceOnce once;
     if (once.needed()) {
-      e = cudaFuncSetAttribute(knn_cells_kernel<K, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      e = cudaFuncSetAttribute(knn_cells_kernel<K, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
       if (e != cudaSuccess) return (int)e;
       once.done();
     }
-    knn_cells_kernel<K, T, true><<<grid, T, list + stage, s>>>(blobs, n, G, kout, drop, hint, hint_k, idx, dist, min(kreq, n));
+    knn_cells_kernel<K, T, true><<<grid, T, list + stage, s>>>(blobs, n, ncap, kout, drop, hint, hint_k, idx, dist, min(kreq, n));
   } else {
-    knn_cells_kernel<K, T, false><<<grid, T, list, s>>>(blobs, n, G, kout, drop, hint, hint_k, idx, dist, min(kreq, n));
+    static PerDeviceOnce once;
+    if (once.needed()) {
+      e = cudaFuncSetAttribute(knn_cells_kernel<K, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      once.done();
+    }
+    knn_cells_kernel<K, T, false><<<grid, T, list, s>>>(blobs, n, ncap, kout, drop, hint, hint_k, idx, dist, min(kreq, n));
   }
   return GEOA3_LAUNCH_RESULT();
 }
@@ -430,42 +578,52 @@ static int launch_knn_cells_k(const unsigned char* blobs, int b, int n, int G, i
 }  // namespace geoa3
 
 extern "C" int geoa3_cell_grid_max(int n) {
-  // largest G whose sorting pass fits one CTA's shared memory
-  int g = 1;
-  while (g < 32 && geoa3::kc_sort_smem(n, (g + 1) * (g + 1) * (g + 1)) <= 220 * 1024) ++g;
-  return g;
+  // largest cell-table capacity whose sorting pass fits one CTA's shared memory
+  if (n < 1) return 0;
+  int lo = 1, hi = 65536;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (geoa3::kc_sort_smem(n, mid) <= 220 * 1024) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
-extern "C" size_t geoa3_cell_blob_bytes(int n, int G) { return geoa3::kc_blob_bytes(n, G * G * G); }
+extern "C" size_t geoa3_cell_blob_bytes(int n, int ncap) { return geoa3::kc_blob_bytes(n, ncap); }
 
-extern "C" int geoa3_cell_sort(const float* pc, int b, int n, int G, void* blobs, geoa3_stream_t stream) {
+extern "C" int geoa3_cell_sort(const float* pc, int b, int n, int ncap, float kref, int gx, int gy, int gz, void* blobs,
+                               geoa3_stream_t stream) {
   using namespace geoa3;
-  GEOA3_CHECK_ARG(pc && blobs && b > 0 && n > 0 && G >= 1);
-  if (n > 65535 || b > 65535 || G > geoa3_cell_grid_max(n)) return GEOA3_EUNSUPPORTED;
+  GEOA3_CHECK_ARG(pc && blobs && b > 0 && n > 0 && ncap >= 1 && gx >= 0 && gy >= 0 && gz >= 0);
+  const bool fixed = gx > 0 || gy > 0 || gz > 0;
+  if (fixed) GEOA3_CHECK_ARG(gx > 0 && gy > 0 && gz > 0);
+  else GEOA3_CHECK_ARG(kref > 0.f);
+  if (n > 65535 || b > 65535 || ncap > geoa3_cell_grid_max(n)) return GEOA3_EUNSUPPORTED;
+  if (fixed && (gx > 64 || gy > 64 || gz > 64 || (long long)gx * gy * gz > ncap)) return GEOA3_EUNSUPPORTED;
   GEOA3_CHECK_ARG((reinterpret_cast<uintptr_t>(blobs) & 15) == 0);
-  const size_t smem = kc_sort_smem(n, G * G * G);
+  const size_t smem = kc_sort_smem(n, ncap);
   static PerDeviceOnce once;
   if (once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(cell_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return (int)e;
     once.done();
   }
-  cell_sort_kernel<<<b, KC_SORT_THREADS, smem, (cudaStream_t)stream>>>(pc, n, G, reinterpret_cast<unsigned char*>(blobs));
+  cell_sort_kernel<<<b, KC_SORT_THREADS, smem, (cudaStream_t)stream>>>(pc, n, ncap, kref, gx, gy, gz,
+                                                                      reinterpret_cast<unsigned char*>(blobs));
   return GEOA3_LAUNCH_RESULT();
 }
 
-extern "C" int geoa3_knn_cells(const void* blobs, int b, int n, int G, int K, int drop, const int32_t* hint, int hint_k,
+extern "C" int geoa3_knn_cells(const void* blobs, int b, int n, int ncap, int K, int drop, const int32_t* hint, int hint_k,
                                int32_t* idx, float* dist, geoa3_stream_t stream) {
   using namespace geoa3;
   GEOA3_CHECK_ARG(blobs && idx);
-  GEOA3_CHECK_ARG(b > 0 && n > 0 && G >= 1 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
+  GEOA3_CHECK_ARG(b > 0 && n > 0 && ncap >= 1 && K > 0 && drop >= 0 && drop < K && hint_k >= 0);
   GEOA3_CHECK_ARG((reinterpret_cast<uintptr_t>(blobs) & 15) == 0);
-  if (K > GEOA3_KNN_MAX_K || b > 65535 || n > 65535 || G > 32) return GEOA3_EUNSUPPORTED;
+  if (K > GEOA3_KNN_MAX_K || b > 65535 || n > 65535 || ncap > 65536) return GEOA3_EUNSUPPORTED;
   if (K > n) return GEOA3_EINVAL;
   const unsigned char* bl = reinterpret_cast<const unsigned char*>(blobs);
   cudaStream_t s = (cudaStream_t)stream;
   const int kout = K - drop;
-#define GEOA3_KC_ARGS bl, b, n, G, K, kout, drop, hint, hint_k, idx, dist, s
+#define GEOA3_KC_ARGS bl, b, n, ncap, K, kout, drop, hint, hint_k, idx, dist, s
   if (K <= 3) return launch_knn_cells_k<3>(GEOA3_KC_ARGS);
   if (K <= 5) return launch_knn_cells_k<5>(GEOA3_KC_ARGS);
   if (K <= 9) return launch_knn_cells_k<9>(GEOA3_KC_ARGS);

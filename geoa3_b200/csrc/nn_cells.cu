@@ -20,11 +20,12 @@
 namespace geoa3 {
 
 constexpr int NC_THREADS = 256;
+constexpr int NC_ROWS = 12;  // row-table slots per query; a query with more non-empty rows walks row by row
 
 struct NcDir {
   const unsigned char* qblobs;  // blobs of the query cloud (queries are taken in ITS cell order)
   const unsigned char* cblobs;  // blobs of the candidate cloud
-  int nq, gq, nc, gc;           // points / cells per axis of the two clouds
+  int nq, qcap, nc, ccap;       // points / cell-table capacity of the query cloud and of the candidate cloud
   const int32_t* hint;          // [b][nq] seed candidate per ORIGINAL query index (nullable; may alias idx)
   float* dist;                  // [b][nq]
   int32_t* idx;                 // [b][nq]
@@ -39,12 +40,12 @@ nn_cells_kernel(const NcDir d0, const NcDir d1) {
   const NcDir& D = dir1 ? d1 : d0;
   const int tile = (int)blockIdx.x - (dir1 ? d0.tiles : 0);
   const int cloud = blockIdx.y, tid = threadIdx.x;
-  const int nq = D.nq, m = D.nc, G = D.gc;
-  const int ncell = G * G * G;
+  const int nq = D.nq, m = D.nc;
+  const int ncell = D.ccap;
   const size_t cbytes = kc_blob_bytes(m, ncell);
   kc_stage_issue(&nc_bar, nc_smem, D.cblobs + (size_t)cloud * cbytes, (unsigned)cbytes);
 
-  const unsigned char* qblob = D.qblobs + (size_t)cloud * kc_blob_bytes(nq, D.gq * D.gq * D.gq);
+  const unsigned char* qblob = D.qblobs + (size_t)cloud * kc_blob_bytes(nq, D.qcap);
   const int slot = tile * NC_THREADS + tid;  // position in the query cloud's cell order
   const bool live = slot < nq;
   const float4 q = reinterpret_cast<const float4*>(qblob + KC_HDR)[min(slot, nq - 1)];
@@ -58,7 +59,8 @@ nn_cells_kernel(const NcDir d0, const NcDir d1) {
   const unsigned acs = (unsigned)__cvta_generic_to_shared(nc_smem + kc_cs_off(m));
   const unsigned aip = (unsigned)__cvta_generic_to_shared(nc_smem + kc_ip_off(m, ncell));
   const float lox = sgp[0], loy = sgp[1], loz = sgp[2], ihx = sgp[3], ihy = sgp[4], ihz = sgp[5];
-  const float hy = sgp[7], hz = sgp[8], gm1 = sgp[10];
+  const float hy = sgp[7], hz = sgp[8], gmx = sgp[10], gmy = sgp[11], gmz = sgp[12];
+  const int gx = (int)sgp[13], gy = (int)sgp[14];  // the candidate cloud's grid (cells per axis)
   // slack covers the rounding of q +- r as well: the query need not lie inside the candidate cloud's box
   const float slack = fmaf(8e-6f, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z)), sgp[9]);
 
@@ -72,48 +74,89 @@ nn_cells_kernel(const NcDir d0, const NcDir d1) {
   int z0 = 0, y0 = 0, nz = -1, ny = -1;
   if (live) {
     const float r = (best < 3e38f ? kc_sqrt(best * KC_REL) * KC_REL : KC_INF) + slack;
-    z0 = kc_cell(q.z - r, loz, ihz, gm1);
-    nz = kc_cell(q.z + r, loz, ihz, gm1) - z0;
-    y0 = kc_cell(q.y - r, loy, ihy, gm1);
-    ny = kc_cell(q.y + r, loy, ihy, gm1) - y0;
+    z0 = kc_cell(q.z - r, loz, ihz, gmz);
+    nz = kc_cell(q.z + r, loz, ihz, gmz) - z0;
+    y0 = kc_cell(q.y - r, loy, ihy, gmy);
+    ny = kc_cell(q.y + r, loy, ihy, gmy) - y0;
   }
   const int wz = __reduce_max_sync(0xffffffffu, nz), wy = __reduce_max_sync(0xffffffffu, ny);
-  for (int oz = 0; oz <= wz; ++oz) {
-    const int rz = z0 + min(oz, max(nz, 0));
-    const float zl = fmaf((float)rz, hz, loz);
-    const float ez = fmaxf(fmaxf(zl - q.z, q.z - (zl + hz)) - slack, 0.f);  // lower bound of |c.z - q.z| in this slab
-    const float ez2 = ez * ez;
+  // One row of cells: the x interval that what is left of `bound` after the row's y/z slab distance can reach.
+  auto row_range = [&](int oz, int oy, float bound, int& s, int& len) {
+    const int rz = z0 + min(oz, max(nz, 0)), ry = y0 + min(oy, max(ny, 0));
+    const float zl = fmaf((float)rz, hz, loz), yl = fmaf((float)ry, hy, loy);
+    const float ez = fmaxf(fmaxf(zl - q.z, q.z - ((float)rz >= gmz ? KC_INF : zl + hz)) - slack, 0.f);  // lower bound of |c.z - q.z| in this slab
+    const float ey = fmaxf(fmaxf(yl - q.y, q.y - ((float)ry >= gmy ? KC_INF : yl + hy)) - slack, 0.f);
+    const float rem = (oz <= nz && oy <= ny) ? fmaf(bound, KC_REL, 1e-37f) - ez * ez - ey * ey : -1.f;
+    const float rx = (rem < 3e38f ? kc_sqrt(fmaxf(rem, 0.f)) * KC_REL : KC_INF) + slack;
+    const unsigned ab = acs + (unsigned)((rz * gy + ry) * gx) * 2u;
+    const int x0 = kc_cell(q.x - rx, lox, ihx, gmx), x1 = kc_cell(q.x + rx, lox, ihx, gmx);
+    s = (int)kc_lds16(ab + x0 * 2);
+    len = rem >= 0.f ? (int)kc_lds16(ab + x1 * 2 + 2) - s : 0;
+  };
+  // (distance, index) as ONE 64-bit key: non-negative floats order like their bit patterns, so the lexicographic rule
+  // "(d < best) or (d == best and index < argbest)" is a single unsigned 64-bit minimum
+  unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bidx;
+  auto fold = [&](bool on, const float4 c) {
+    const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);  // the pinned arithmetic decides
+    const unsigned long long k2 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(c.w);
+    key = (on && k2 < key) ? k2 : key;
+  };
+
+  // phase 1: the lane's non-empty rows within reach of the SEED distance -> row table (first position | length << 16)
+  const unsigned t0 = (unsigned)__cvta_generic_to_shared(nc_smem + cbytes) + tid * 4;
+  unsigned tp = t0;
+  int tot = 0, nrow = 0;
+  for (int oz = 0; oz <= wz; ++oz)
     for (int oy = 0; oy <= wy; ++oy) {
-      const int ry = y0 + min(oy, max(ny, 0));
-      const float yl = fmaf((float)ry, hy, loy);
-      const float ey = fmaxf(fmaxf(yl - q.y, q.y - (yl + hy)) - slack, 0.f);
-      // what the CURRENT best leaves for (c.x - q.x)^2 in this row
-      const float rem = (oz <= nz && oy <= ny) ? fmaf(best, KC_REL, 1e-37f) - ez2 - ey * ey : -1.f;
-      const float rx = (rem < 3e38f ? kc_sqrt(fmaxf(rem, 0.f)) * KC_REL : KC_INF) + slack;
-      const unsigned ab = acs + (unsigned)((rz * G + ry) * G) * 2u;
-      const int x0 = kc_cell(q.x - rx, lox, ihx, gm1), x1 = kc_cell(q.x + rx, lox, ihx, gm1);
-      const int s = (int)kc_lds16(ab + x0 * 2);
-      const int len = rem >= 0.f ? (int)kc_lds16(ab + x1 * 2 + 2) - s : 0;
-      const int wl = __reduce_max_sync(0xffffffffu, len);
-      const unsigned ca = a4 + (unsigned)s * 16u;
-      const unsigned cl = ca + (unsigned)max(len - 1, 0) * 16u;  // reads past the lane's own range are clamped to it
-      auto fold = [&](int i, const float4 c) {
-        const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);  // the pinned arithmetic decides
-        const int ci = __float_as_int(c.w);
-        const bool better = i < len && (d < best || (d == best && ci < bidx));
-        best = better ? d : best;
-        bidx = better ? ci : bidx;
-      };
-      int i = 0;
-      for (; i + 1 < wl; i += 2) {
-        const float4 c0 = kc_lds128(min(ca + (unsigned)i * 16u, cl));
-        const float4 c1 = kc_lds128(min(ca + (unsigned)i * 16u + 16u, cl));
-        fold(i, c0);
-        fold(i + 1, c1);
+      int s, len;
+      row_range(oz, oy, best, s, len);
+      if (len > 0) {
+        if (nrow < NC_ROWS) kc_sts32(tp, (unsigned)s | ((unsigned)len << 16));
+        tp += NC_THREADS * 4;
+        ++nrow;
+        tot += len;
       }
-      if (i < wl) fold(i, kc_lds128(min(ca + (unsigned)i * 16u, cl)));
+    }
+  const bool big = nrow > NC_ROWS;  // a far-off seed: this lane takes the row-by-row walk below
+  kc_sts32(t0 + min(nrow, NC_ROWS) * (NC_THREADS * 4), 0xffff0000u);  // sentinel: a finished lane idles on it
+  if (big) tot = 0;
+  // phase 2: every lane walks its own candidate stream; the warp runs as long as its longest stream
+  {
+    const int wtot = __reduce_max_sync(0xffffffffu, tot);
+    const unsigned aend = a4 + (unsigned)(m - 1) * 16u;
+    unsigned ca = a4;
+    int left = 0;
+    tp = t0;
+#pragma unroll 2
+    for (int it = 0; it < wtot; ++it) {
+      if (left == 0) {
+        const unsigned e = kc_lds32(tp);
+        tp += NC_THREADS * 4;
+        ca = a4 + (e & 0xffffu) * 16u;
+        left = (int)(e >> 16);
+      }
+      const float4 c = kc_lds128(min(ca, aend));
+      ca += 16u;
+      --left;
+      fold(it < tot, c);
     }
   }
+  // row-by-row walk (rare): rows are re-derived from the CURRENT best, which shrinks as candidates are folded in
+  if (__any_sync(0xffffffffu, big)) {
+    for (int oz = 0; oz <= wz; ++oz)
+      for (int oy = 0; oy <= wy; ++oy) {
+        int s, len;
+        row_range(oz, oy, __uint_as_float((unsigned)(key >> 32)), s, len);
+        if (!big) len = 0;
+        const int wl = __reduce_max_sync(0xffffffffu, len);
+        const unsigned ca = a4 + (unsigned)s * 16u;
+        const unsigned cl = ca + (unsigned)max(len - 1, 0) * 16u;
+#pragma unroll 1
+        for (int i = 0; i < wl; ++i) fold(i < len, kc_lds128(min(ca + (unsigned)i * 16u, cl)));
+      }
+  }
+  best = __uint_as_float((unsigned)(key >> 32));
+  bidx = (int)(unsigned)key;
   if (live) {
     D.dist[(size_t)cloud * nq + qo] = best;
     D.idx[(size_t)cloud * nq + qo] = bidx;
@@ -122,24 +165,25 @@ nn_cells_kernel(const NcDir d0, const NcDir d1) {
 
 }  // namespace geoa3
 
-extern "C" int geoa3_nn_pair_cells(const void* blobs_adv, const void* blobs_ori, int b, int n, int m, int g_adv, int g_ori,
+extern "C" int geoa3_nn_pair_cells(const void* blobs_adv, const void* blobs_ori, int b, int n, int m, int ncap_adv, int ncap_ori,
                                    const int32_t* hint_a2o, const int32_t* hint_o2a, float* d_a2o, int32_t* jstar,
                                    float* d_o2a, int32_t* istar, geoa3_stream_t stream) {
   using namespace geoa3;
-  GEOA3_CHECK_ARG(blobs_adv && blobs_ori && d_a2o && jstar && b > 0 && n > 0 && m > 0 && g_adv >= 1 && g_ori >= 1);
+  GEOA3_CHECK_ARG(blobs_adv && blobs_ori && d_a2o && jstar && b > 0 && n > 0 && m > 0 && ncap_adv >= 1 && ncap_ori >= 1);
   GEOA3_CHECK_ARG((d_o2a == nullptr) == (istar == nullptr));
   GEOA3_CHECK_ARG(((reinterpret_cast<uintptr_t>(blobs_adv) | reinterpret_cast<uintptr_t>(blobs_ori)) & 15) == 0);
-  if (b > 65535 || n > 65535 || m > 65535 || g_adv > 32 || g_ori > 32) return GEOA3_EUNSUPPORTED;
+  if (b > 65535 || n > 65535 || m > 65535 || ncap_adv > 65536 || ncap_ori > 65536) return GEOA3_EUNSUPPORTED;
   const bool both = d_o2a != nullptr;
-  const size_t smem = max(kc_blob_bytes(m, g_ori * g_ori * g_ori), both ? kc_blob_bytes(n, g_adv * g_adv * g_adv) : (size_t)0);
+  size_t smem = max(kc_blob_bytes(m, ncap_ori), both ? kc_blob_bytes(n, ncap_adv) : (size_t)0);
+  smem += (size_t)(NC_ROWS + 1) * NC_THREADS * 4;       // + the row tables
   if (smem > 226 * 1024) return GEOA3_EUNSUPPORTED;  // the candidate blob has to fit one CTA's shared memory
   NcDir d0, d1;
   d0.qblobs = reinterpret_cast<const unsigned char*>(blobs_adv);
   d0.cblobs = reinterpret_cast<const unsigned char*>(blobs_ori);
-  d0.nq = n; d0.gq = g_adv; d0.nc = m; d0.gc = g_ori;
+  d0.nq = n; d0.qcap = ncap_adv; d0.nc = m; d0.ccap = ncap_ori;
   d0.hint = hint_a2o; d0.dist = d_a2o; d0.idx = jstar; d0.tiles = ceil_div(n, NC_THREADS);
   d1.qblobs = d0.cblobs; d1.cblobs = d0.qblobs;
-  d1.nq = m; d1.gq = g_ori; d1.nc = n; d1.gc = g_adv;
+  d1.nq = m; d1.qcap = ncap_ori; d1.nc = n; d1.ccap = ncap_adv;
   d1.hint = hint_o2a; d1.dist = d_o2a; d1.idx = istar; d1.tiles = both ? ceil_div(m, NC_THREADS) : 0;
   static PerDeviceOnce once;
   if (once.needed()) {

@@ -64,7 +64,7 @@ class HintBuffers(object):
         # identical to the scanning kernels; use_cells=False keeps those (A/B measurements, tests).
         self.use_cells = use_cells
         self.knn_k = 16  # neighbourhood size the adversarial grid is sized for (set by the fused loss node)
-        self.cells_ori = self.cells_adv = None   # (blobs, G)
+        self.cells_ori = self.cells_adv = None   # ops.Cells
         # visiting order for the pruned searches (ops.visit_order of the ORIGINAL cloud), computed once (first call)
         self.perm = self.iperm = self.ori_arranged = None
         self.prune_min_n_knn = prune_min_n_knn  # measured: box pruning of the kNN scan only pays for larger clouds
@@ -94,24 +94,27 @@ class HintBuffers(object):
     def cells_ok(self, n, m):
         return self.use_cells and 32 <= n <= self.CELLS_MAX_N and 32 <= m <= self.CELLS_MAX_N
 
-    def ensure_cells(self, ori, k=16):
-        """Blob of the ORIGINAL cloud (static during an attack) + the buffer the adversarial blob is rebuilt into."""
+    KREF_NN = 4.0  # the 1-NN balls of an attack step are small: the original cloud gets a finer grid (measured)
+
+    def ensure_cells(self, ori):
+        """Cells of the ORIGINAL cloud (static during an attack)."""
         b, _, m = ori.shape
-        if self.cells_ori is None or self.cells_ori[0].shape[0] != b or self.cells_ori[2] != m:
-            g = ops.cell_grid_size(m, 8)      # 1-NN balls are small: a finer grid than the kNN one (measured)
-            self.cells_ori = (ops.cell_sort(ori, g), g, m)
+        if self.cells_ori is None or self.cells_ori.blobs.shape[0] != b or self.cells_ori.n != m:
+            self.cells_ori = ops.cell_sort(ori, kref=self.KREF_NN)
 
     def refresh_cells(self, ori):
-        if self.cells_ori is not None and self.cells_ori[0].shape[0] == ori.shape[0] and self.cells_ori[2] == ori.shape[2]:
-            ops.cell_sort(ori, self.cells_ori[1], out=self.cells_ori[0])
+        c = self.cells_ori
+        if c is not None and c.blobs.shape[0] == ori.shape[0] and c.n == ori.shape[2]:
+            ops.cell_sort(ori, kref=self.KREF_NN, out=c)
 
     def sort_adv(self, adv, k=16):
+        """Cells of the adversarial cloud, rebuilt every step into the same buffer (grid sized for the kNN balls)."""
         b, _, n = adv.shape
-        g = ops.cell_grid_size(n, k + 1)
-        if self.cells_adv is None or self.cells_adv[0].shape[0] != b or self.cells_adv[2] != n or self.cells_adv[1] != g:
-            self.cells_adv = (ops.cell_sort(adv, g), g, n)
+        c = self.cells_adv
+        if c is None or c.blobs.shape[0] != b or c.n != n:
+            self.cells_adv = ops.cell_sort(adv, kref=k + 1)
         else:
-            ops.cell_sort(adv, g, out=self.cells_adv[0])
+            ops.cell_sort(adv, kref=k + 1, out=c)
         return self.cells_adv
 
     def ensure_nn(self, b, n, m, dev):
@@ -266,8 +269,7 @@ def _launch_nn_hinted(e, hb):
         hb.ensure_cells(e.ori_c)
         e.cells = hb.sort_adv(e.adv_c, hb.knn_k)
         e.arr = None
-        ops.nn_pair_cells(e.cells[0], hb.cells_ori[0], n, m, e.cells[1], hb.cells_ori[1], hint_a2o=hj, hint_o2a=hi,
-                          out=(hb.d1, hb.jstar, hb.d2, hb.istar))
+        ops.nn_pair_cells(e.cells, hb.cells_ori, hint_a2o=hj, hint_o2a=hi, out=(hb.d1, hb.jstar, hb.d2, hb.istar))
     elif n == m:  # both clouds share the visiting order of the original cloud (adv_i is a perturbed ori_i)
         hb.ensure_order(e.ori_c)
         # ONE launch arranges adv into the visiting order and boxes its groups: both pruned searches of the step use it
@@ -290,8 +292,8 @@ def _launch_knn_hinted(e, k, hb):
     hint = hb.frozen["nbr"][k] if hb.frozen else buf
     n = e.adv_c.shape[2]
     cells = getattr(e, "cells", None)
-    if cells is not None and cells[1] == ops.cell_grid_size(n, k + 1):
-        ops.knn_cells(cells[0], n, cells[1], k + 1, drop=1, hint=hint, out=buf)
+    if cells is not None:
+        ops.knn_cells(cells, k + 1, drop=1, hint=hint, out=buf)
         return
     ordered = hb.perm is not None and n == hb.perm.shape[1]
     arr = getattr(e, "arr", None)

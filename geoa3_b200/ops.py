@@ -166,29 +166,43 @@ def knn(query, ref, K, drop=0, return_dist=False, hint=None, out=None, perm_q=No
     return idx, dist
 
 
-def cell_grid_size(n, K):
-    """Cells per axis for the cell-grid kNN: the cell edge is about the expected K-NN radius of a surface-sampled
-    cloud (area ~ 4 pi: r = sqrt(4K/n) in units of the half extent).  Any G gives the same result; this one was the
-    fastest in the sweep of profiles/knn_cells_r2.md."""
-    g = int(round(2.0 / math.sqrt(4.0 * K / max(n, 1))))
-    return max(1, min(g, _lib.load().geoa3_cell_grid_max(n), 32))
+class Cells(object):
+    """Cell-grid blobs of a batch of clouds (geoa3_cell_sort): blobs uint8 [b, blob_bytes], n points, table capacity."""
+    __slots__ = ("blobs", "n", "ncap")
+
+    def __init__(self, blobs, n, ncap):
+        self.blobs, self.n, self.ncap = blobs, n, ncap
 
 
-def cell_sort(pc, G, out=None):
-    """pc [b,3,n] -> per-cloud cell-grid blobs (uint8 [b, blob_bytes]) for `knn_cells` (geoa3_cell_sort)."""
+def cell_table_capacity(n):
+    """Default capacity of the cell table: room for ~2 cells per point (cells hold ~5 points on a surface; thin or
+    clustered clouds need the slack), within what the sorting pass can keep in shared memory."""
+    return int(max(64, min(2 * n, 8192, _lib.load().geoa3_cell_grid_max(n))))
+
+
+def cell_sort(pc, kref=17.0, grid=None, ncap=None, out=None):
+    """pc [b,3,n] -> Cells for `knn_cells` / `nn_pair_cells`.  grid=None: per-cloud cubic cells sized for balls of `kref`
+    points (the search it will serve: K for kNN lists, a few points for 1-NN); grid=g or (gx,gy,gz): that grid.
+    `out`: a Cells object of the same geometry to rebuild in place (CUDA-graph friendly)."""
     require_cuda_f32(pc, "pc")
     b, _, n = pc.shape
-    nb = _lib.load().geoa3_cell_blob_bytes(n, G)
-    blobs = out if out is not None else torch.empty(b, nb, device=pc.device, dtype=torch.uint8)
+    gx, gy, gz = (0, 0, 0) if grid is None else ((int(grid),) * 3 if isinstance(grid, int) else tuple(int(g) for g in grid))
+    if out is not None:
+        ncap = out.ncap
+    elif ncap is None:
+        ncap = max(cell_table_capacity(n), gx * gy * gz)
+    nb = _lib.load().geoa3_cell_blob_bytes(n, ncap)
+    blobs = out.blobs if out is not None else torch.empty(b, nb, device=pc.device, dtype=torch.uint8)
     with _guard(pc):
         _count(1)
-        check(_lib.load().geoa3_cell_sort(ptr(pc), b, n, G, ptr(blobs), stream(pc)))
-    return blobs
+        check(_lib.load().geoa3_cell_sort(ptr(pc), b, n, ncap, float(kref), gx, gy, gz, ptr(blobs), stream(pc)))
+    return out if out is not None else Cells(blobs, n, ncap)
 
 
-def knn_cells(blobs, n, G, K, drop=0, return_dist=False, hint=None, out=None):
-    """Self-kNN member sets from the cell-grid blobs of `cell_sort`: idx [b,n,K-drop] i32 in ORIGINAL numbering (rows by
-    original query index, members in ascending cell-arrangement position), dist | None.  Exact for any hint / G."""
+def knn_cells(cells, K, drop=0, return_dist=False, hint=None, out=None):
+    """Self-kNN member sets from the Cells of `cell_sort`: idx [b,n,K-drop] i32 in ORIGINAL numbering (rows by original
+    query index, members in ascending cell-arrangement position), dist | None.  Exact for any hint / grid."""
+    blobs, n = cells.blobs, cells.n
     b = blobs.shape[0]
     idx = out if out is not None else torch.empty(b, n, K - drop, device=blobs.device, dtype=torch.int32)
     hk = 0
@@ -198,13 +212,15 @@ def knn_cells(blobs, n, G, K, drop=0, return_dist=False, hint=None, out=None):
     dist = torch.empty(b, n, K - drop, device=blobs.device, dtype=torch.float32) if return_dist else None
     with _guard(blobs):
         _count(1)
-        check(_lib.load().geoa3_knn_cells(ptr(blobs), b, n, G, K, drop, ptr(hint), hk, ptr(idx), ptr(dist), stream(blobs)))
+        check(_lib.load().geoa3_knn_cells(ptr(blobs), b, n, cells.ncap, K, drop, ptr(hint), hk, ptr(idx), ptr(dist),
+                                          stream(blobs)))
     return idx, dist
 
 
-def nn_pair_cells(blobs_adv, blobs_ori, n, m, g_adv, g_ori, both=True, hint_a2o=None, hint_o2a=None, out=None):
-    """nn_pair over cell-grid blobs (geoa3_nn_pair_cells): -> d_a2o [b,n], jstar [b,n], d_o2a [b,m] | None, istar | None."""
-    b, dev = blobs_adv.shape[0], blobs_adv.device
+def nn_pair_cells(cells_adv, cells_ori, both=True, hint_a2o=None, hint_o2a=None, out=None):
+    """nn_pair over Cells (geoa3_nn_pair_cells): -> d_a2o [b,n], jstar [b,n], d_o2a [b,m] | None, istar | None."""
+    n, m = cells_adv.n, cells_ori.n
+    b, dev = cells_adv.blobs.shape[0], cells_adv.blobs.device
     if out is not None:
         d1, j1, d2, i2 = out
     else:
@@ -215,10 +231,11 @@ def nn_pair_cells(blobs_adv, blobs_ori, n, m, g_adv, g_ori, both=True, hint_a2o=
     for h, nm in ((hint_a2o, "hint_a2o"), (hint_o2a, "hint_o2a")):
         if h is not None:
             require_cuda_i32(h, nm)
-    with _guard(blobs_adv):
+    with _guard(cells_adv.blobs):
         _count(1)
-        check(_lib.load().geoa3_nn_pair_cells(ptr(blobs_adv), ptr(blobs_ori), b, n, m, g_adv, g_ori, ptr(hint_a2o),
-                                              ptr(hint_o2a), ptr(d1), ptr(j1), ptr(d2), ptr(i2), stream(blobs_adv)))
+        check(_lib.load().geoa3_nn_pair_cells(ptr(cells_adv.blobs), ptr(cells_ori.blobs), b, n, m, cells_adv.ncap,
+                                              cells_ori.ncap, ptr(hint_a2o), ptr(hint_o2a), ptr(d1), ptr(j1), ptr(d2),
+                                              ptr(i2), stream(cells_adv.blobs)))
     return d1, j1, d2, i2
 
 

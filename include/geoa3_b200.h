@@ -100,38 +100,47 @@ GEOA3_API int geoa3_knn_set(const float *query, const float *ref, int b, int n, 
                             const int32_t *perm_q, const int32_t *perm_c, const int32_t *iperm_c, const float *bb_c,
                             const int32_t *hint, int hint_k, int32_t *idx, float *dist, geoa3_stream_t stream);
 
-/* Cell-grid form of the same member search for SELF queries (the curvature term's neighbour lists, refreshed every
- * attack step): geoa3_cell_sort arranges each cloud [b][3][n] into G^3 uniform cells of its bounding box (one CTA per
- * cloud, stable counting sort: cell-major, ascending original index inside a cell) and writes one self-contained blob
- * per cloud (geoa3_cell_blob_bytes(n, G) bytes, 16-byte aligned: grid parameters, the cloud as float4 (x, y, z,
- * original index) in cell order, the cell start table, the inverse permutation).  geoa3_knn_cells then visits, per
- * query, only the cell rows its search ball can reach (ball radius^2 = the largest pinned distance to the hinted
- * candidates; without a usable hint the search starts from +inf and is still exact) and keeps every candidate whose
- * PINNED distance is inside the bound; the K smallest (distance, original index) keys minus the `drop` smallest are
- * the members.  Same members as geoa3_knn / geoa3_knn_set for ANY hint and ANY G (bit-exact membership and
- * distances); they are written in ascending position of the cell arrangement — a function of the cloud and G only.
+/* Cell-grid searches (the attack step's 1-NN and kNN searches on clouds of up to 65535 points).
+ *
+ * geoa3_cell_sort arranges each cloud [b][3][n] into a uniform grid of CUBIC cells over its bounding box (one CTA per
+ * cloud, counting sort: cell (cz*gy + cy)*gx + cx major, ascending original index inside a cell — so the cells of one
+ * (cz, cy) row are one contiguous range of positions) and writes one self-contained blob per cloud
+ * (geoa3_cell_blob_bytes(n, ncap) bytes, 16-byte aligned: grid parameters, the cloud as float4 (x, y, z, original
+ * index) in cell order, the cell start table, the inverse permutation).  ncap is the capacity of the cell table (it
+ * fixes the blob layout; <= geoa3_cell_grid_max(n): the sorting pass keeps its tables in one CTA's shared memory).
+ * Grid: gx, gy, gz > 0 -> that many cells per axis (gx*gy*gz <= ncap, <= 64 per axis), cell edge = longest side of the
+ * box / largest g.  gx = gy = gz = 0 -> chosen PER CLOUD: cell edge ~ radius of a ball holding `kref` points, from the
+ * cloud's surface density (occupied cells of a 16^3 probe grid), as many cells per axis as the box needs within ncap —
+ * a thin rod and a sphere both get cells that match their own neighbourhood size.  The grid only affects speed.
+ *
+ * geoa3_knn_cells (SELF queries: the curvature term's neighbour lists) visits, per query, only the cell rows its search
+ * ball can reach (radius^2 = the largest pinned distance to the hinted candidates; without a usable hint the search
+ * starts from +inf and is still exact) and keeps every candidate whose PINNED distance is inside the bound; the K
+ * smallest (distance, original index) keys minus the `drop` smallest are the members.  Same members as geoa3_knn /
+ * geoa3_knn_set for ANY hint and ANY grid (bit-exact membership and distances); they are written in ascending
+ * position of the cell arrangement — a function of the cloud and its grid only, never of the hint.
  * idx [b][n][K-drop] (rows by ORIGINAL query index), dist nullable; hint [b][n][hint_k] may alias idx.
- * n <= 65535; G <= geoa3_cell_grid_max(n) (the sorting pass keeps its tables in one CTA's shared memory).
  * Replaces: knn_points(pc, pc, K=k+1).idx[..., 1:] inside _get_kappa_adv, Lib/loss_utils.py:77-78 (no counterpart
  * for the grid in the reference: its search is pytorch3d's unordered brute force). */
 GEOA3_API int geoa3_cell_grid_max(int n);
-GEOA3_API size_t geoa3_cell_blob_bytes(int n, int G);
-GEOA3_API int geoa3_cell_sort(const float *pc, int b, int n, int G, void *blobs, geoa3_stream_t stream);
-GEOA3_API int geoa3_knn_cells(const void *blobs, int b, int n, int G, int K, int drop, const int32_t *hint, int hint_k,
+GEOA3_API size_t geoa3_cell_blob_bytes(int n, int ncap);
+GEOA3_API int geoa3_cell_sort(const float *pc, int b, int n, int ncap, float kref, int gx, int gy, int gz, void *blobs,
+                              geoa3_stream_t stream);
+GEOA3_API int geoa3_knn_cells(const void *blobs, int b, int n, int ncap, int K, int drop, const int32_t *hint, int hint_k,
                               int32_t *idx, float *dist, geoa3_stream_t stream);
 
-/* geoa3_nn_pair on the cell-grid blobs of geoa3_cell_sort (blobs_adv: n points, g_adv cells per axis; blobs_ori: m,
- * g_ori): the same outputs, bit for bit — d_a2o[i], jstar[i] = (min, lowest argmin) over ori of the pinned distance to
- * adv point i, d_o2a / istar the other direction (both NULL to skip it) — for ANY seed and ANY grids.  A query walks
+/* geoa3_nn_pair on the cell-grid blobs of geoa3_cell_sort (blobs_adv: n points, table capacity ncap_adv; blobs_ori: m,
+ * ncap_ori): the same outputs, bit for bit — d_a2o[i], jstar[i] = (min, lowest argmin) over ori of the pinned distance
+ * to adv point i, d_o2a / istar the other direction (both NULL to skip it) — for ANY seed and ANY grids.  A query walks
  * only the cell rows within sqrt(best) of itself, best starting at the pinned distance to its seed (hint_*, default:
  * the same index; may alias the index output).  In an attack step that is ~10 candidates per query.  The candidate
- * blob must fit one CTA's shared memory (<= 226 KB: clouds up to ~11 000 points); otherwise GEOA3_EUNSUPPORTED
- * (use geoa3_nn_pair).  The original cloud's blob is built once per attack, the adversarial one every step (it also
- * serves geoa3_knn_cells).
+ * blob must fit one CTA's shared memory (clouds up to ~10 000 points); otherwise GEOA3_EUNSUPPORTED (use
+ * geoa3_nn_pair).  The original cloud's blob is built once per attack, the adversarial one every step (it also serves
+ * geoa3_knn_cells).
  * Replaces: knn_points(adv, ori, K=1) + knn_points(ori, adv, K=1), Lib/loss_utils.py:32-33,41,48,70,92. */
-GEOA3_API int geoa3_nn_pair_cells(const void *blobs_adv, const void *blobs_ori, int b, int n, int m, int g_adv, int g_ori,
-                                  const int32_t *hint_a2o, const int32_t *hint_o2a, float *d_a2o, int32_t *jstar,
-                                  float *d_o2a, int32_t *istar, geoa3_stream_t stream);
+GEOA3_API int geoa3_nn_pair_cells(const void *blobs_adv, const void *blobs_ori, int b, int n, int m, int ncap_adv,
+                                  int ncap_ori, const int32_t *hint_a2o, const int32_t *hint_o2a, float *d_a2o,
+                                  int32_t *jstar, float *d_o2a, int32_t *istar, geoa3_stream_t stream);
 
 /* Bounding boxes of a cloud that is already arranged in visiting order: per cloud geoa3_group_bbox_floats(n)
  * floats = [G0 + G1][8] (lo xyz, hi xyz, max |p|^2, pad), G0 = ceil(n/32) boxes of 32 consecutive positions

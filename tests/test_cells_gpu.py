@@ -39,7 +39,7 @@ def knn_cases():
 
 @pytest.mark.parametrize("name,pts,K", knn_cases(), ids=[c[0] for c in knn_cases()])
 def test_knn_cells_members_exact(name, pts, K):
-    from geoa3_b200 import _lib, ops
+    from geoa3_b200 import ops
 
     rng = np.random.default_rng(5)
     b, _, n = pts.shape
@@ -51,12 +51,11 @@ def test_knn_cells_members_exact(name, pts, K):
     stale = cu(O.knn(pts + 0.05, pts[:, :, ::-1].copy(), K)[0][:, :, 1:])
     junk = cu(rng.integers(-3, n + 50, (b, n, K - 1)).astype(np.int32))
     zeros = torch.zeros(b, n, K - 1, dtype=torch.int32, device="cuda")
-    gmax = _lib.load().geoa3_cell_grid_max(n)
-    for G in sorted({1, 2, 5, ops.cell_grid_size(n, K), min(gmax, 13)}):
-        blobs = ops.cell_sort(P, G)
+    for G in [1, 2, (5, 1, 3), None, 13, (9, 1, 12), ("kref", 3.0), ("kref", 60.0)]:
+        cells = ops.cell_sort(P, kref=G[1]) if isinstance(G, tuple) and G[0] == "kref" else ops.cell_sort(P, kref=K, grid=G)
         first = None
         for h, tag in ((None, "none"), (exact, "exact"), (stale, "stale"), (junk, "junk"), (zeros, "dup")):
-            idx, dist = ops.knn_cells(blobs, n, G, K, drop=1, return_dist=True, hint=h)
+            idx, dist = ops.knn_cells(cells, K, drop=1, return_dist=True, hint=h)
             i_, d_ = idx.cpu().numpy(), dist.cpu().numpy()
             o = np.argsort(d_.view(np.int32).astype(np.int64) * 65536 + i_, -1)
             assert np.array_equal(np.take_along_axis(i_, o, -1), want_i), (name, G, tag)
@@ -64,13 +63,12 @@ def test_knn_cells_members_exact(name, pts, K):
             first = idx if first is None else first
             assert torch.equal(idx, first), (name, G, tag, "member order depends on the hint")
     # drop = 0 keeps the self match; in place: the buffer is hint and output at once, three refreshes of a moving cloud
-    G = ops.cell_grid_size(n, K)
-    idx0 = ops.knn_cells(ops.cell_sort(P, G), n, G, K, drop=0)[0]
+    idx0 = ops.knn_cells(ops.cell_sort(P, kref=K), K, drop=0)[0]
     assert np.array_equal(np.sort(idx0.cpu().numpy(), -1), np.sort(oi, -1))
     buf, cur = exact.clone(), pts
     for step in range(3):
         cur = (cur + synth.make_offsets(b, n, seed=40 + step, std=3e-3)).astype(np.float32)
-        ops.knn_cells(ops.cell_sort(cu(cur), G), n, G, K, drop=1, hint=buf, out=buf)
+        ops.knn_cells(ops.cell_sort(cu(cur), kref=K), K, drop=1, hint=buf, out=buf)
         assert np.array_equal(np.sort(buf.cpu().numpy(), -1), np.sort(O.knn(cur, cur, K)[0][:, :, 1:], -1))
 
 
@@ -91,7 +89,7 @@ def nn_cases():
 
 @pytest.mark.parametrize("name,adv,ori", nn_cases(), ids=[c[0] for c in nn_cases()])
 def test_nn_pair_cells_bitexact(name, adv, ori):
-    from geoa3_b200 import _lib, ops
+    from geoa3_b200 import ops
 
     rng = np.random.default_rng(7)
     adv, ori = np.ascontiguousarray(adv, np.float32), np.ascontiguousarray(ori, np.float32)
@@ -100,22 +98,20 @@ def test_nn_pair_cells_bitexact(name, adv, ori):
     od1, oj1 = O.nn1(adv, ori)
     od2, oi2 = O.nn1(ori, adv)
     A, Oc = cu(adv), cu(ori)
-    for ga, go in ((1, 1), (3, 5), (ops.cell_grid_size(n, 17), ops.cell_grid_size(m, 8)), (13, 11)):
-        ga = min(ga, _lib.load().geoa3_cell_grid_max(n))
-        go = min(go, _lib.load().geoa3_cell_grid_max(m))
-        ba, bo = ops.cell_sort(A, ga), ops.cell_sort(Oc, go)
+    for ga, go in ((1, 1), ((3, 1, 4), 5), (None, None), (13, (11, 1, 7))):
+        ba, bo = ops.cell_sort(A, kref=17, grid=ga), ops.cell_sort(Oc, kref=4, grid=go)
         hints = [(None, None, "none"), (cu(oj1), cu(oi2), "exact"),
                  (cu(rng.integers(-3, m + 50, (b, n)).astype(np.int32)), cu(rng.integers(-3, n + 50, (b, m)).astype(np.int32)), "junk"),
                  (torch.zeros(b, n, dtype=torch.int32, device="cuda"), torch.zeros(b, m, dtype=torch.int32, device="cuda"), "zeros")]
         for h1, h2, tag in hints:
-            d1, j1, d2, i2 = ops.nn_pair_cells(ba, bo, n, m, ga, go, hint_a2o=h1, hint_o2a=h2)
+            d1, j1, d2, i2 = ops.nn_pair_cells(ba, bo, hint_a2o=h1, hint_o2a=h2)
             assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2), (name, ga, go, tag)
             assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2), (name, ga, go, tag)
-        d1, j1, d2, i2 = ops.nn_pair_cells(ba, bo, n, m, ga, go, both=False)
+        d1, j1, d2, i2 = ops.nn_pair_cells(ba, bo, both=False)
         assert d2 is None and np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(d1.cpu().numpy(), od1)
         # in place: hint and output are the same buffer
         j, i = cu(oj1).clone(), cu(oi2).clone()
-        ops.nn_pair_cells(ba, bo, n, m, ga, go, hint_a2o=j, hint_o2a=i, out=(d1, j, torch.empty_like(i, dtype=torch.float32), i))
+        ops.nn_pair_cells(ba, bo, hint_a2o=j, hint_o2a=i, out=(d1, j, torch.empty_like(i, dtype=torch.float32), i))
         assert np.array_equal(j.cpu().numpy(), oj1) and np.array_equal(i.cpu().numpy(), oi2)
 
 
@@ -126,16 +122,28 @@ def test_cell_blob_layout():
     from geoa3_b200 import ops
 
     pts = make(3, 1000, 2, 2e-2)[0]
-    n, G = 1000, 7
+    n = 1000
     P = cu(pts)
-    blobs = ops.cell_sort(P, G)
-    assert blobs.shape[1] == ops._lib.load().geoa3_cell_blob_bytes(n, G) and blobs.shape[1] % 16 == 0
+    for grid in ((7, 5, 6), None):
+        _check_blob(ops, pts, P, n, grid)
+
+
+def _check_blob(ops, pts, P, n, grid):
+    cells = ops.cell_sort(P, kref=17, grid=grid)
+    blobs, nc = cells.blobs, cells.ncap
+    assert blobs.shape[1] == ops._lib.load().geoa3_cell_blob_bytes(n, nc) and blobs.shape[1] % 16 == 0
     for _ in range(3):
-        assert torch.equal(ops.cell_sort(P, G), blobs)
+        assert torch.equal(ops.cell_sort(P, kref=17, grid=grid).blobs, blobs)
+    again = ops.cell_sort(P, kref=17, grid=grid, out=cells)
+    assert again is cells
     raw = blobs.cpu().numpy()
-    nc = G ** 3
     for c in range(pts.shape[0]):
-        gp = raw[c, :48].view(np.float32)
+        gp = raw[c, :64].view(np.float32)
+        G = tuple(int(g) for g in gp[13:16])
+        assert np.array_equal(gp[10:13], np.float32(G) - 1) and G[0] * G[1] * G[2] <= nc
+        if grid is not None:
+            assert G == tuple(grid)
+        ncell = G[0] * G[1] * G[2]
         cl = raw[c, 64:64 + 16 * n].view(np.float32).reshape(n, 4)
         orig = cl[:, 3].view(np.int32)
         cs0 = 64 + 16 * n
@@ -145,10 +153,10 @@ def test_cell_blob_layout():
         assert np.array_equal(np.sort(orig), np.arange(n))
         assert np.array_equal(cl[:, :3], pts[c].T[orig])
         assert np.array_equal(ipos[orig], np.arange(n))
-        assert cstart[0] == 0 and cstart[nc] == n and np.all(np.diff(cstart) >= 0)
+        assert cstart[0] == 0 and cstart[nc] == n and np.all(np.diff(cstart) >= 0) and np.all(cstart[ncell:] == n)
         lo, inv_h = gp[0:3], gp[3:6]
-        cell = np.clip(((cl[:, :3] - lo) * inv_h).astype(np.float32), 0, G - 1).astype(np.int64)
-        key = (cell[:, 2] * G + cell[:, 1]) * G + cell[:, 0]
+        cell = np.clip(((cl[:, :3] - lo) * inv_h).astype(np.float32), 0, np.float32(G) - 1).astype(np.int64)
+        key = (cell[:, 2] * G[1] + cell[:, 1]) * G[0] + cell[:, 0]
         assert np.all(np.diff(key) >= 0)
         assert np.array_equal(np.searchsorted(key, np.arange(nc + 1), side="left"), cstart)
         same = np.diff(key) == 0

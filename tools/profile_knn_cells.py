@@ -15,30 +15,30 @@ from geoa3_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=250)
 ap.add_argument("--steps", type=int, default=80)
-ap.add_argument("--grid", type=int, default=8)
+ap.add_argument("--kref", type=float, default=17)
 ap.add_argument("--k", type=int, default=16)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 st, pins = bench.build_state("PointNet", a.batch, bench.NPTS, 0, a.batch, dev)
 for _ in range(a.steps):
     st.step()
-k, n, G = a.k, bench.NPTS, a.grid
+k, n = a.k, bench.NPTS
 adv = (st.base + st.offset).detach().contiguous()
 hint = st.hints.nbr[k].clone()
 out = torch.empty_like(hint)
-blobs = ops.cell_sort(adv, G)
-ops.knn_cells(blobs, n, G, k + 1, drop=1, hint=hint, out=out)
+blobs = ops.cell_sort(adv, kref=a.kref)
+ops.knn_cells(blobs, k + 1, drop=1, hint=hint, out=out)
 ori = st.pc_ori.detach().contiguous()
-bo = ops.cell_sort(ori, G)
+bo = ops.cell_sort(ori, kref=4)
 hb = st.hints
 hj, hi = hb.jstar.clone(), hb.istar.clone()
 outs = (torch.empty_like(hb.d1), torch.empty_like(hj), torch.empty_like(hb.d2), torch.empty_like(hi))
-ops.nn_pair_cells(blobs, bo, n, n, G, G, hint_a2o=hj, hint_o2a=hi, out=outs)
+ops.nn_pair_cells(blobs, bo, hint_a2o=hj, hint_o2a=hi, out=outs)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-ops.cell_sort(adv, G, out=blobs)
-ops.nn_pair_cells(blobs, bo, n, n, G, G, hint_a2o=hj, hint_o2a=hi, out=outs)
-ops.knn_cells(blobs, n, G, k + 1, drop=1, hint=hint, out=out)
+ops.cell_sort(adv, kref=a.kref, out=blobs)
+ops.nn_pair_cells(blobs, bo, hint_a2o=hj, hint_o2a=hi, out=outs)
+ops.knn_cells(blobs, k + 1, drop=1, hint=hint, out=out)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("done")
