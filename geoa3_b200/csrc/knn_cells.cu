@@ -32,7 +32,7 @@
 #define KC_EXTRA 11
 #endif
 #ifndef KC_THREADS
-#define KC_THREADS 512
+#define KC_THREADS 256
 #endif
 #ifndef KC_HSCALE
 #define KC_HSCALE 1.0f   // cell edge / estimated radius of a kref-point ball (speed only)
@@ -447,10 +447,10 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int ncap, int k
         if (pass) lp += T * 2;
       }
     }
-    if (fa) {
+    {  // (all lanes of the warp: the cooperative output below shuffles)
       const int cnt = (int)(lp - l0) / (T * 2);
       const int kt = kk - (drop == 1 ? 1 : 0);
-      bool good = !bad && cnt >= kt && cnt <= R;
+      bool good = fa && !bad && cnt >= kt && cnt <= R;
       if (good) {  // the members' distances, into the scratch column (the row table is no longer needed)
         float dm = KC_INF;
         for (int s2 = 0; s2 < cnt; ++s2) {
@@ -461,11 +461,40 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int ncap, int k
         }
         good = drop != 1 || dm > 0.f;  // a zero-distance neighbour competes with the query for being the dropped key
       }
-      if (good) {
-        kc_mark<T>(d_, v_, cnt, cnt - kt);
-        kc_write<T>(d_, v_, cnt, kout, io, dn);
-        careful = false;
+      if (good) kc_mark<T>(d_, v_, cnt, cnt - kt);
+      // Output.  Per-thread stores would touch 32 different rows per instruction (4 bytes of 32 sectors each: the L1
+      // store path then costs 32 cycles per instruction, ~25 % of the whole kernel); instead every thread compacts its
+      // live members to the front of its list column and the warp writes 8 rows of 64 bytes per instruction (int4 per
+      // lane, 4 lanes per row for kout = 16).  Other kout / an optional distance output / short clouds: plain stores.
+      const int lpr = kout >> 2;  // lanes per row
+      const bool coop = dist_out == nullptr && kk == K && (kout & 3) == 0 && lpr >= 1 && lpr <= 32 && (32 % lpr) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(idx_out) & 15) == 0);
+      if (good && !coop) kc_write<T>(d_, v_, cnt, kout, io, dn);
+      if (coop) {
+        if (good) {
+          int o = 0;
+          for (int s2 = 0; s2 < cnt; ++s2) {
+            const uint16_t vi = v_[s2 * T];
+            if (d_[s2 * T] >= 0.f) { v_[o * T] = vi; ++o; }  // o <= s2: in place
+          }
+        }
+        __syncwarp();
+        const int lane = tid & 31, sub = lane % lpr, rpi = 32 / lpr;  // rows per instruction
+        const uint16_t* vw = v_ - lane;  // column of lane 0 of this warp
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+          const int row = r0 + lane / lpr;
+          const int rqo = __shfl_sync(0xffffffffu, qo, row);
+          const bool rgood = __shfl_sync(0xffffffffu, (int)good, row) != 0;
+          if (rgood) {
+            int4 m4;
+            m4.x = vw[(sub * 4 + 0) * T + row]; m4.y = vw[(sub * 4 + 1) * T + row];
+            m4.z = vw[(sub * 4 + 2) * T + row]; m4.w = vw[(sub * 4 + 3) * T + row];
+            *reinterpret_cast<int4*>(idx_out + ((size_t)cloud * n + rqo) * kout + sub * 4) = m4;
+          }
+        }
+        __syncwarp();
       }
+      if (good) careful = false;
     }
   }
 
