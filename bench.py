@@ -367,12 +367,19 @@ def sweep_record(dev):
             t_prune = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm), 3, 1)
             t_set = time_events(lambda: ops.knn(adv, adv, k + 1, drop=1, hint=hn, perm_q=pm, perm_c=pm, iperm_c=ipm,
                                                 members_only=True), 3, 1)
+            t_cells = t_sort = None
+            if n <= 4096:   # the cell-grid search (the attack step uses it up to HintBuffers.CELLS_MAX_N points)
+                cells = ops.cell_sort(adv, kref=k + 1)
+                t_sort = time_events(lambda: ops.cell_sort(adv, kref=k + 1, out=cells), 3, 1)
+                t_cells = time_events(lambda: ops.knn_cells(cells, k + 1, drop=1, hint=hn), 3, 1)
             nbr = ops.knn(adv, adv, k + 1, drop=1, hint=hn)[0]
             t_kap = time_events(lambda: ops.kappa_loss_fwd(adv, normal=nrm, jstar=js, nbr=nbr), 3, 1)
-            best = min(t_hint, t_prune, t_set)
+            best = min(t_hint, t_prune, t_set, (t_cells + t_sort) if t_cells is not None else 1e30)
             byts = (28 + 4 * k) * B * n
             rows.append({"n": n, "k": k, "knn_us": round(t_plain, 1), "knn_hinted_us": round(t_hint, 1),
                          "knn_hinted_pruned_us": round(t_prune, 1), "knn_members_hinted_pruned_us": round(t_set, 1),
+                         "knn_cells_us": None if t_cells is None else round(t_cells, 1),
+                         "cell_sort_us": None if t_sort is None else round(t_sort, 1),
                          "kappa_us": round(t_kap, 1),
                          "hbm_frac": round(byts / ((best + t_kap) * 1e-6) / 1e9 / pk["hbm_gbs"], 5),
                          "fp32_tflops": round(8.0 * B * n * n / (best * 1e-6) / 1e12, 2)})
@@ -728,7 +735,7 @@ def main():
         kb = kernel_breakdown(pc_keep, nrm_keep, adv[0], adv[1], KNN)
         pk = peaks()
         top = max(kb, key=kb.get)
-        alg_bytes = {"arrange": 28 * b * n, "nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n,
+        alg_bytes = {"arrange": 28 * b * n, "cell_sort": 34 * b * n, "nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n,
                      "knn_kappa": (12 + 4 * KNN + 24) * b * n, "kappa_loss_fwd": (36 + 4 * KNN) * b * n,
                      "loss_reduce": 20 * b * n, "loss_bwd": (56 + 4 * KNN) * b * n}.get(top, 52 * b * n)
         alg_flop = {"nn_pair": 16.0 * b * n * n, "knn": 8.0 * b * n * n, "knn_kappa": 8.0 * b * n * n}.get(top, 0.0)
@@ -737,7 +744,9 @@ def main():
         line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic().get(top), "peak_source": pk["source"],
                             "algorithmic_bytes_per_launch": alg_bytes,
-                            "note": "distance kernels are FP32-issue bound (SURVEY §8d); see fp32",
+                            "note": "the search kernels are instruction-issue / shared-memory-latency bound, not HBM bound "
+                                    "(SURVEY §8d); fp32 = flops of the full n x n scan the kernel REPLACES / its time (the "
+                                    "cell walk evaluates ~5 % of those pairs)",
                             "fp32": {"achieved_tflops": alg_flop / t_s / 1e12, "peak_tflops": pk["fp32_tflops"],
                                      "frac": alg_flop / t_s / 1e12 / pk["fp32_tflops"],
                                      "peak_source": "ubench/fp32_peak.cu measured on this pool"}}
