@@ -737,7 +737,8 @@ def main():
         top = max(kb, key=kb.get)
         alg_bytes = {"arrange": 28 * b * n, "cell_sort": 34 * b * n, "nn_pair": 40 * b * n, "knn": (12 + 4 * KNN) * b * n,
                      "knn_kappa": (12 + 4 * KNN + 24) * b * n, "kappa_loss_fwd": (36 + 4 * KNN) * b * n,
-                     "loss_reduce": 20 * b * n, "loss_bwd": (56 + 4 * KNN) * b * n}.get(top, 52 * b * n)
+                     "loss_reduce": 20 * b * n, "loss_bwd": (56 + 4 * KNN) * b * n,
+                     "geo_fwd_bwd": (84 + 4 * KNN) * b * n}.get(top, 52 * b * n)
         alg_flop = {"nn_pair": 16.0 * b * n * n, "knn": 8.0 * b * n * n, "knn_kappa": 8.0 * b * n * n}.get(top, 0.0)
         t_s = kb[top] * 1e-6
         achieved = alg_bytes / t_s / 1e9

@@ -32,6 +32,8 @@ SIGNATURES = {
     "geoa3_kappa_loss_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geoa3_loss_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "geoa3_loss_bwd": (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "geoa3_geo_fwd_bwd_supported": (_i, [_i, _i, _i]),
+    "geoa3_geo_fwd_bwd": (_i, [_vp] * 7 + [_i, _vp, _vp, _f, _f, _f, _i, _i, _i] + [_vp] * 8),
     "geoa3_furthest_point_sampling": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "geoa3_farthest_points_sample": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "geoa3_gather_points": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -14,7 +14,10 @@
 
 namespace geoa3 {
 
-constexpr int KL_THREADS = 512;   // forward: one CTA per cloud
+#ifndef KL_THREADS_N
+#define KL_THREADS_N 512
+#endif
+constexpr int KL_THREADS = KL_THREADS_N;   // forward: one CTA per cloud
 constexpr int KL_WARPS = KL_THREADS / 32;
 constexpr int BW_THREADS = 1024;  // backward: one CTA per cloud, one target per thread at n = 1024
 constexpr int BW_WARPS = BW_THREADS / 32;
@@ -411,6 +414,212 @@ static bool bwd_fused_ok(int n, int m, int k, bool do_curv, bool do_col, BwdLayo
   return plan_bwd_layout(n, m, k, do_curv, do_col, L);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One kernel per attack step for everything that follows the two searches: kappa_i with borrowed normals, the CD / HD /
+// curvature reductions AND the gradient of  w_cd*CD + w_hd*HD + w_cu*CUR  for a unit upstream gradient per cloud (the
+// loss is linear in its upstream gradient, so autograd's backward is a scale by g[b]).  Same arithmetic as
+// kappa_loss_fwd_kernel followed by loss_bwd_kernel — the cloud, the normals and the neighbour rows are staged / fetched
+// once, and one launch (with its per-cloud ramp-up) disappears.  Requires the fused shared-memory layout (plan_bwd_layout).
+template <int WARPS>
+__device__ __forceinline__ float block_sum_w(float v, float* scratch) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < WARPS; ++i) t += scratch[i];
+  return t;
+}
+
+
+__global__ void __launch_bounds__(BW_THREADS, 2)
+geo_fwd_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori, const float* __restrict__ normal,
+                   const float* __restrict__ kappa_ori, const int32_t* __restrict__ jstar,
+                   const int32_t* __restrict__ istar, const int32_t* __restrict__ nbr, int k,
+                   const float* __restrict__ d_a2o, const float* __restrict__ d_o2a, float w_cd, float w_hd, float w_cu,
+                   int n, int m, float* __restrict__ cd, float* __restrict__ hd, float* __restrict__ curv,
+                   float* __restrict__ kappa_out, float* __restrict__ nrm_out, int32_t* __restrict__ hd_arg_out,
+                   float* __restrict__ grad_adv, BwdLayout lay) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* pts = reinterpret_cast<float4*>(smem_raw + lay.pts);
+  float4* nrm = reinterpret_cast<float4*>(smem_raw + lay.nrm);
+  int* offs1 = reinterpret_cast<int*>(smem_raw + lay.offs1);
+  int* offs2 = reinterpret_cast<int*>(smem_raw + lay.offs2);
+  int* whist = reinterpret_cast<int*>(smem_raw + lay.whist);
+  uint16_t* ent1 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent1);
+  uint16_t* ent2 = reinterpret_cast<uint16_t*>(smem_raw + lay.ent2);
+  __shared__ int scan_scratch[BW_WARPS + 1];
+  __shared__ float s_f[BW_WARPS];
+  __shared__ int s_i[BW_WARPS];
+  __shared__ int s_ha;
+
+  const int cloud = blockIdx.x, tid = threadIdx.x;
+  const float* a = adv + (size_t)cloud * 3 * n;
+  const float* o = ori + (size_t)cloud * 3 * m;
+  const bool do_curv = k > 0 && nbr != nullptr && w_cu != 0.f;
+  const bool do_col = istar != nullptr && w_cd != 0.f;
+  const float* nb = normal + (size_t)cloud * 3 * m;
+
+  // ---- stage the cloud and the borrowed normals
+  for (int i = tid; i < n; i += BW_THREADS) {
+    const size_t gi = (size_t)cloud * n + i;
+    if (do_curv) {
+      const int js = jstar[gi];
+      const float nx = nb[js], ny = nb[m + js], nz = nb[2 * m + js];
+      nrm[i] = make_float4(nx, ny, nz, 0.f);
+      if (nrm_out) {
+        float* no = nrm_out + (size_t)cloud * 3 * n;
+        no[i] = nx; no[n + i] = ny; no[2 * n + i] = nz;
+      }
+    }
+    pts[i] = make_float4(a[i], a[n + i], a[2 * n + i], 0.f);
+  }
+  __syncthreads();
+
+  // ---- forward: kappa_i, per-cloud sums (the arithmetic of kappa_loss_fwd_kernel)
+  float* gkf = reinterpret_cast<float*>(whist);  // per-point curvature factors (the CSR build reuses this array later)
+  float s1 = 0.f, sc = 0.f, mx = -1.f;
+  int am = 0x7fffffff;
+  const float inv_k = k > 0 ? 1.f / (float)k : 0.f;
+#pragma unroll 1
+  for (int i = tid; i < n; i += BW_THREADS) {
+    float gki = 0.f;
+    {
+      const size_t gi = (size_t)cloud * n + i;
+      if (do_curv) {
+        const float4 pi = pts[i];
+        const float4 ni = nrm[i];
+        const int32_t* nbi = nbr + gi * k;
+        float acc = 0.f;
+        auto term = [&](int j) {
+          const float4 pj = pts[j];
+          const float vx = pj.x - pi.x, vy = pj.y - pi.y, vz = pj.z - pi.z;
+          const float s2 = vx * vx + vy * vy + vz * vz;
+          const float inv = s2 >= 1e-24f ? rsqrtf(s2) : 1e12f;
+          acc += fabsf((vx * ni.x + vy * ni.y + vz * ni.z) * inv);
+        };
+        if ((k & 3) == 0) {
+          const int4* nb4 = reinterpret_cast<const int4*>(nbi);
+          const int k4 = k >> 2;
+          for (int t = 0; t < k4; t += 2) {  // (32 registers per thread: two index quads in flight)
+            const int4 q0 = nb4[t];
+            const int4 q1 = t + 1 < k4 ? nb4[t + 1] : make_int4(0, 0, 0, 0);
+            term(q0.x); term(q0.y); term(q0.z); term(q0.w);
+            if (t + 1 < k4) { term(q1.x); term(q1.y); term(q1.z); term(q1.w); }
+          }
+        } else {
+          for (int t = 0; t < k; ++t) term(nbi[t]);
+        }
+        const float kap = acc * inv_k;
+        if (kappa_out) kappa_out[gi] = kap;
+        const float e = kap - kappa_ori[(size_t)cloud * m + jstar[gi]];
+        sc += e * e;
+        gki = w_cu * (2.f / (float)n) * e;
+      }
+      const float d = d_a2o[gi];
+      s1 += d;
+      if (d > mx) { mx = d; am = i; }  // ascending i per thread + strict '>' keeps the lowest index
+    }
+    gkf[i] = gki;
+  }
+  float s2 = 0.f;
+  if (d_o2a)
+    for (int j = tid; j < m; j += BW_THREADS) s2 += d_o2a[(size_t)cloud * m + j];
+  const float t1 = block_sum_w<BW_WARPS>(s1, s_f);
+  const float t2 = d_o2a ? block_sum_w<BW_WARPS>(s2, s_f) : 0.f;
+  const float tc = do_curv ? block_sum_w<BW_WARPS>(sc, s_f) : 0.f;
+  {  // arg-max with the lowest index on ties
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, mx, of);
+      const int oi = __shfl_xor_sync(0xffffffffu, am, of);
+      if (ov > mx || (ov == mx && oi < am)) { mx = ov; am = oi; }
+    }
+    const int w = tid >> 5, l = tid & 31;
+    __syncthreads();
+    if (l == 0) { s_f[w] = mx; s_i[w] = am; }
+    __syncthreads();
+    if (tid == 0) {
+      float v = s_f[0];
+      int ix = s_i[0];
+      for (int i = 1; i < BW_WARPS; ++i)
+        if (s_f[i] > v || (s_f[i] == v && s_i[i] < ix)) { v = s_f[i]; ix = s_i[i]; }
+      s_ha = ix;
+      if (cd) cd[cloud] = t1 / (float)n + (d_o2a ? t2 / (float)m : 0.f);
+      if (hd) hd[cloud] = v;
+      if (hd_arg_out) hd_arg_out[cloud] = ix;
+      if (curv) curv[cloud] = do_curv ? tc / (float)n : 0.f;
+    }
+  }
+  // every kappa gather is done: the per-point curvature factors may now sit next to the coordinates
+  for (int i = tid; i < n; i += BW_THREADS) pts[i].w = gkf[i];
+  __syncthreads();
+
+  // ---- backward (the gather of loss_bwd_kernel, upstream gradient 1 per cloud)
+  if (do_curv)
+    build_csr_sorted<BW_THREADS, uint16_t>(nbr + (size_t)cloud * n * k, n * k, n, lay.k_magic, offs1, whist, ent1,
+                                           scan_scratch);
+  if (do_col)
+    build_csr_sorted<BW_THREADS, uint16_t>(istar + (size_t)cloud * m, m, n, 0u, offs2, whist, ent2, scan_scratch);
+  const int ha = w_hd != 0.f ? s_ha : -1;
+  const float w_row = w_cd * (2.f / (float)n), w_col = w_cd * (2.f / (float)m);
+  for (int p = tid; p < n; p += BW_THREADS) {
+    const size_t gp = (size_t)cloud * n + p;
+    const float4 ap = pts[p];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (w_cd != 0.f || ha == p) {
+      const int js = jstar[gp];
+      const float rx = ap.x - o[js], ry = ap.y - o[m + js], rz = ap.z - o[2 * m + js];
+      if (w_cd != 0.f) { gx = w_row * rx; gy = w_row * ry; gz = w_row * rz; }
+      if (do_col) {
+        const int e1 = offs2[p + 1];
+        for (int e = offs2[p]; e < e1; ++e) {
+          const int j = ent2[e];
+          gx += w_col * (ap.x - o[j]); gy += w_col * (ap.y - o[m + j]); gz += w_col * (ap.z - o[2 * m + j]);
+        }
+      }
+      if (ha == p) { gx += w_hd * 2.f * rx; gy += w_hd * 2.f * ry; gz += w_hd * 2.f * rz; }
+    }
+    if (do_curv) {
+      const float4 np_ = nrm[p];
+      const float f0 = ap.w * inv_k;
+      const int32_t* nbp = nbr + gp * k;
+      float ox = 0.f, oy = 0.f, oz = 0.f;
+      if ((k & 3) == 0) {
+        for (int t = 0; t < k; t += 4) {
+          const int4 j4 = *reinterpret_cast<const int4*>(nbp + t);
+          const int js4[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 aj = pts[js4[u]];
+            const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
+            ox += dv.x; oy += dv.y; oz += dv.z;
+          }
+        }
+      } else {
+        for (int t = 0; t < k; ++t) {
+          const float4 aj = pts[nbp[t]];
+          const float3 dv = dkappa_dv(aj.x - ap.x, aj.y - ap.y, aj.z - ap.z, np_.x, np_.y, np_.z, f0);
+          ox += dv.x; oy += dv.y; oz += dv.z;
+        }
+      }
+      gx -= ox; gy -= oy; gz -= oz;
+      const int e1 = offs1[p + 1];
+      for (int e = offs1[p]; e < e1; ++e) {
+        const int i = ent1[e];
+        const float4 ai = pts[i];
+        const float4 ni = nrm[i];
+        const float3 dv = dkappa_dv(ap.x - ai.x, ap.y - ai.y, ap.z - ai.z, ni.x, ni.y, ni.z, ai.w * inv_k);
+        gx += dv.x; gy += dv.y; gz += dv.z;
+      }
+    }
+    float* g = grad_adv + (size_t)cloud * 3 * n;
+    g[p] = gx; g[n + p] = gy; g[2 * n + p] = gz;
+  }
+}
+
 }  // namespace geoa3
 
 
@@ -505,5 +714,37 @@ extern "C" int geoa3_loss_bwd(const float* adv, const float* ori, const float* n
   if ((err = GEOA3_LAUNCH_RESULT())) return err;
   bwd_large_gather_kernel<<<grid, 256, 0, s>>>(ori, jstar, nbr, hd_arg, g_cd, g_hd, n, m, k, do_curv, do_col, ws, G,
                                               grad_adv);
+  return GEOA3_LAUNCH_RESULT();
+}
+
+extern "C" int geoa3_geo_fwd_bwd_supported(int n, int m, int k) {
+  using namespace geoa3;
+  BwdLayout L;
+  return n > 0 && m > 0 && k >= 0 && k <= 32 && bwd_fused_ok(n, m, k, k > 0, true, &L) && L.total <= 227 * 1024 - 1024 ? 1 : 0;
+}
+
+extern "C" int geoa3_geo_fwd_bwd(const float* adv, const float* ori, const float* normal, const float* kappa_ori,
+                                 const int32_t* jstar, const int32_t* istar, const int32_t* nbr, int k, const float* d_a2o,
+                                 const float* d_o2a, float w_cd, float w_hd, float w_cu, int b, int n, int m, float* cd,
+                                 float* hd, float* curv, float* kappa, float* nrm_out, int32_t* hd_arg, float* grad_adv,
+                                 geoa3_stream_t stream) {
+  using namespace geoa3;
+  GEOA3_CHECK_ARG(adv && ori && jstar && d_a2o && grad_adv && b > 0 && n > 0 && m > 0 && k >= 0);
+  GEOA3_CHECK_ARG((istar == nullptr) == (d_o2a == nullptr));
+  const bool do_curv = k > 0 && nbr != nullptr && w_cu != 0.f;
+  if (do_curv) GEOA3_CHECK_ARG(normal && kappa_ori);
+  if (b > 65535 || !geoa3_geo_fwd_bwd_supported(n, m, do_curv ? k : 0)) return GEOA3_EUNSUPPORTED;
+  BwdLayout L;
+  if (!bwd_fused_ok(n, m, do_curv ? k : 0, do_curv, istar != nullptr && w_cd != 0.f, &L)) return GEOA3_EUNSUPPORTED;
+  if (L.total > 227 * 1024 - 1024) return GEOA3_EUNSUPPORTED;  // (this kernel has 400 bytes of static shared memory)
+  static PerDeviceOnce attr_done;
+  if (attr_done.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(geo_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done.done();
+  }
+  geo_fwd_bwd_kernel<<<b, BW_THREADS, L.total, (cudaStream_t)stream>>>(adv, ori, normal, kappa_ori, jstar, istar, nbr,
+                                                                      do_curv ? k : 0, d_a2o, d_o2a, w_cd, w_hd, w_cu, n, m,
+                                                                      cd, hd, curv, kappa, nrm_out, hd_arg, grad_adv, L);
   return GEOA3_LAUNCH_RESULT();
 }

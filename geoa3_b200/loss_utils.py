@@ -322,6 +322,14 @@ def _launch_geo_fwd(e, nrm_src, kappa_ori, nbr, single_side, use_curv):
         want_kappa=use_curv, want_nrm=use_curv, want_cd=True, want_hd=True, want_curv=use_curv)
 
 
+FUSE_FWD_BWD = True  # geo_loss: one geoa3_geo_fwd_bwd launch instead of kappa_loss_fwd + loss_bwd (A/B switch for tests)
+
+
+def _launch_geo_fused(e, nrm_src, kappa_ori, nbr, single_side, w_cd, w_hd, w_cu):
+    return ops.geo_fwd_bwd(e.adv_c, e.ori_c, nrm_src, kappa_ori, e.jstar, None if single_side else e.istar, nbr, e.d1,
+                           None if single_side else e.d2, w_cd, w_hd, w_cu)
+
+
 def _launch_geo_bwd(e, out, nbr, kappa_ori, g_cd, g_hd, g_cu, single_side):
     return ops.loss_bwd(e.adv_c, ori=e.ori_c, nrm_adv=out["nrm"], kappa_adv=out["kappa"], kappa_ori=kappa_ori,
                         jstar=e.jstar, istar=None if single_side else e.istar, nbr=nbr, hd_arg=out["hd_arg"],
@@ -351,10 +359,11 @@ def step_plan(adv, ori, ori_normal, ori_kappa, k, hints, w=(1.0, 0.1, 1.0)):
         g = g.detach().float().contiguous()
         gs = [(g * w_) .contiguous() for w_ in w]
         pre = [("cell_sort", lambda: _launch_cell_sort(e, hints))] if e.cells is not None else []
-        return pre + [("nn_pair", lambda: _launch_nn_hinted(e, hints)),
-                ("knn", lambda: _launch_knn_hinted(e, k, hints)),
-                ("kappa_loss_fwd", lambda: _launch_geo_fwd(e, nrm_src, ko, nbr, False, True)),
-                ("loss_bwd", lambda: _launch_geo_bwd(e, out, nbr, ko, gs[0], gs[1], gs[2], False))]
+        pre += [("nn_pair", lambda: _launch_nn_hinted(e, hints)), ("knn", lambda: _launch_knn_hinted(e, k, hints))]
+        if FUSE_FWD_BWD and ops.geo_fwd_bwd_supported(e.adv_c.shape[2], e.ori_c.shape[2], k):
+            return pre + [("geo_fwd_bwd", lambda: _launch_geo_fused(e, nrm_src, ko, nbr, False, w[0], w[1], w[2]))]
+        return pre + [("kappa_loss_fwd", lambda: _launch_geo_fwd(e, nrm_src, ko, nbr, False, True)),
+                      ("loss_bwd", lambda: _launch_geo_bwd(e, out, nbr, ko, gs[0], gs[1], gs[2], False))]
 
     return {"out": out, "entry": e, "nbr": nbr, "launches": launches}
 
@@ -441,18 +450,32 @@ class _GeoLoss(torch.autograd.Function):
         use_curv = w_curv != 0 and k > 0
         nbr = _nbr(e, k) if use_curv else None
         ko = ori_kappa.detach().float().contiguous() if use_curv else None
-        out = _launch_geo_fwd(e, _as_input(ori_normal, "ori_normal") if use_curv else None, ko, nbr, single_side, use_curv)
-        cd, hd = out["cd"], out["hd"]
-        curv = out["curv"] if use_curv else torch.zeros_like(cd)
+        n, m = e.adv_c.shape[2], e.ori_c.shape[2]
+        ctx.fused = bool(ctx.needs_input_grad[0]) and FUSE_FWD_BWD and ops.geo_fwd_bwd_supported(n, m, k if use_curv else 0)
+        if ctx.fused:
+            # forward and backward in ONE launch: the gradient for a unit upstream gradient is computed now,
+            # backward() only scales it (the loss is linear in its upstream gradient)
+            out = _launch_geo_fused(e, _as_input(ori_normal, "ori_normal") if use_curv else None, ko, nbr, single_side,
+                                    w_cd, w_hd, w_curv if use_curv else 0.0)
+            cd, hd, curv = out["cd"], out["hd"], out["curv"]
+            ctx.unit_grad = out["grad"]
+        else:
+            out = _launch_geo_fwd(e, _as_input(ori_normal, "ori_normal") if use_curv else None, ko, nbr, single_side, use_curv)
+            cd, hd = out["cd"], out["hd"]
+            curv = out["curv"] if use_curv else torch.zeros_like(cd)
+            ctx.e, ctx.out, ctx.nbr = e, out, nbr
+            ctx.kappa_ori = ko
         total = w_cd * cd + w_hd * hd + (w_curv * curv if use_curv else 0.0)
-        ctx.e, ctx.out, ctx.nbr = e, out, nbr
         ctx.w = (w_cd, w_hd, w_curv, single_side, use_curv)
-        ctx.kappa_ori = ko
         ctx.mark_non_differentiable(cd, hd, curv)
         return total, cd, hd, curv
 
     @staticmethod
     def backward(ctx, g, _a, _b, _c):
+        if ctx.fused:
+            ug = ctx.unit_grad
+            g = g.detach().float().reshape(-1, 1, 1)
+            return (ug * g,) + (None,) * 9
         e, out = ctx.e, ctx.out
         w_cd, w_hd, w_curv, single_side, use_curv = ctx.w
         g = _grad_vec(g, e.adv_c)

@@ -287,6 +287,29 @@ def loss_bwd(adv, ori=None, nrm_adv=None, kappa_adv=None, kappa_ori=None, jstar=
     return grad
 
 
+def geo_fwd_bwd_supported(n, m, k):
+    return bool(_lib.load().geoa3_geo_fwd_bwd_supported(n, m, k))
+
+
+def geo_fwd_bwd(adv, ori, normal, kappa_ori, jstar, istar, nbr, d_a2o, d_o2a, w_cd, w_hd, w_cu):
+    """Fused kappa / CD / HD / curvature forward + unit-upstream backward (geoa3_geo_fwd_bwd) ->
+    dict(cd, hd, curv [b], grad [b,3,n])."""
+    require_cuda_f32(adv, "adv_pc")
+    b, _, n = adv.shape
+    m = ori.shape[2]
+    k = nbr.shape[2] if nbr is not None else 0
+    dev = adv.device
+    out = {"cd": torch.empty(b, device=dev), "hd": torch.empty(b, device=dev), "curv": torch.empty(b, device=dev),
+           "grad": torch.empty_like(adv)}
+    with _guard(adv):
+        _count(1)
+        check(_lib.load().geoa3_geo_fwd_bwd(ptr(adv), ptr(ori), ptr(normal), ptr(kappa_ori), ptr(jstar), ptr(istar),
+                                            ptr(nbr), k, ptr(d_a2o), ptr(d_o2a), float(w_cd), float(w_hd), float(w_cu),
+                                            b, n, m, ptr(out["cd"]), ptr(out["hd"]), ptr(out["curv"]), None, None, None,
+                                            ptr(out["grad"]), stream(adv)))
+    return out
+
+
 def farthest_points_sample_idx(points, nsamples, start):
     """points [b,n,3] f32, start [b] int32 -> idx [b,nsamples] int32: plain FPS from the given first picks
     (geoa3_farthest_points_sample; Lib/utility.py:175-187 semantics)."""

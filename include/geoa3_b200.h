@@ -186,6 +186,23 @@ GEOA3_API int geoa3_loss_bwd(const float *adv, const float *ori, const float *nr
                    const float *g_kappa, int b, int n, int m, int k, float *grad_adv, void *workspace,
                    size_t workspace_bytes, geoa3_stream_t stream);
 
+/* geoa3_kappa_loss_fwd + geoa3_loss_bwd in ONE launch, for the attack step (forward and backward always run
+ * together there): kappa with normals borrowed through jstar, cd / hd / curv per cloud (same definitions as
+ * geoa3_kappa_loss_fwd; outputs nullable, kappa [b][n], nrm_out [b][3][n], hd_arg [b] optional) AND
+ * grad_adv [b][3][n] = d(w_cd*CD + w_hd*HD + w_cu*CUR)/d adv for a UNIT upstream gradient per cloud — the loss is linear in
+ * its upstream gradient, so the caller's backward is a scale by g[b].  normal [b][3][m] / kappa_ori [b][m] live on the
+ * original points; istar / d_o2a both NULL = one-sided CD; k = 0 or w_cu = 0 skips the curvature term.
+ * Same arithmetic and summation orders as the two separate kernels (deterministic, no float atomics); the cloud, the
+ * normals and the neighbour rows are staged once.  Needs the single-kernel shared-memory plan:
+ * geoa3_geo_fwd_bwd_supported(n, m, k) != 0 (n*k <= 65535 edges, n <= ~3 900 at k = 16), else GEOA3_EUNSUPPORTED.
+ * Replaces: Lib/loss_utils.py:28-97 + autograd backward, as assembled by Attacker/geoA3_attack.py:131-162,326. */
+GEOA3_API int geoa3_geo_fwd_bwd_supported(int n, int m, int k);
+GEOA3_API int geoa3_geo_fwd_bwd(const float *adv, const float *ori, const float *normal, const float *kappa_ori,
+                                const int32_t *jstar, const int32_t *istar, const int32_t *nbr, int k, const float *d_a2o,
+                                const float *d_o2a, float w_cd, float w_hd, float w_cu, int b, int n, int m, float *cd,
+                                float *hd, float *curv, float *kappa, float *nrm_out, int32_t *hd_arg, float *grad_adv,
+                                geoa3_stream_t stream);
+
 /* ----------------------------------------------------------------------------------------------
  * pointnet2_ops  (replaces the 9 functions exported by _ext-src/src/bindings.cpp:6-19)
  * ---------------------------------------------------------------------------------------------- */

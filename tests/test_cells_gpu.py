@@ -193,3 +193,40 @@ def test_hint_buffers_cells_equal_scan():
         assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])   # CD, HD: same inputs
         for x, y in zip(outs[0], outs[1]):
             assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max()) + 1e-12
+
+
+@pytest.mark.parametrize("b,n,k,std,single", [(4, 1024, 16, 1e-2, False), (3, 1000, 16, 3e-2, False), (2, 512, 32, 1e-2, True),
+                                              (2, 200, 2, 1e-1, False), (2, 2970, 16, 1e-2, False)])
+def test_fused_fwd_bwd_equals_two_kernels(b, n, k, std, single):
+    """geoa3_geo_fwd_bwd (kappa + reductions + unit-upstream gradient in one launch, scaled in backward) against the
+    two-kernel path (geoa3_kappa_loss_fwd, then geoa3_loss_bwd with the real upstream gradient): same losses, same
+    gradient up to the rounding of (g*w)*x vs g*(w*x), for non-uniform upstream gradients, and bitwise reproducible."""
+    from geoa3_b200 import loss_utils as L
+
+    adv, ori, nrm = make(b, n, 3, std)
+    Oc, Nr = cu(ori), cu(nrm)
+    ko = L._get_kappa_ori(Oc, Nr, k)
+    up = torch.linspace(0.3, 1.7, b, device="cuda")
+    res = {}
+    for fused in (True, False, True):
+        L.FUSE_FWD_BWD = fused
+        try:
+            L.clear_cache()
+            a = cu(adv).requires_grad_(True)
+            tot, cd, hd, cv = L.geo_loss(a, Oc, Nr, ko, k, 1.0, 0.1, 1.0, single_side=single, hints=L.HintBuffers())
+            (tot * up).sum().backward()
+            cur = (tot.detach().clone(), cd.clone(), hd.clone(), cv.clone(), a.grad.clone())
+        finally:
+            L.FUSE_FWD_BWD = True
+        if fused and True in res:
+            assert all(torch.equal(x, y) for x, y in zip(cur, res[True])), "fused path is not reproducible"
+        res[fused] = cur
+    for x, y in zip(res[True][:4], res[False][:4]):
+        assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max()) + 1e-12
+    gf, gu = res[True][4], res[False][4]
+    assert float((gf - gu).abs().max()) <= 2e-6 * float(gu.abs().max())
+    # forward only (no gradient requested): the two-kernel forward runs, same values
+    L.clear_cache()
+    with torch.no_grad():
+        t2 = L.geo_loss(cu(adv), Oc, Nr, ko, k, 1.0, 0.1, 1.0, single_side=single, hints=L.HintBuffers())[0]
+    assert float((t2 - res[False][0]).abs().max()) <= 2e-6 * float(t2.abs().max())
