@@ -3,30 +3,33 @@
 // (pinned distance, ORIGINAL index) pairs minus the `drop` smallest — found by looking only at the cells a query's
 // search ball touches instead of streaming the whole cloud past every query.
 //
-//  geoa3_cell_sort   one CTA per cloud: bounding box, G^3 uniform cells, stable counting sort (cell-major, ascending
-//                    original index inside a cell: csr.cuh) -> the cloud as float4 (x, y, z, original index) in cell
-//                    order, the cell start table and the inverse permutation.  Cell index = (cz*G + cy)*G + cx, so one
-//                    (cz, cy) ROW of cells is one contiguous range of positions.
-//  geoa3_knn_cells   one query per thread, a warp's 32 queries are neighbours in cell order.  tau = largest pinned
-//                    distance to the hinted candidates (previous step's neighbours): an upper bound of the K-th distance
-//                    whenever the hints are K-1 distinct points other than the query (verified at the end: fewer than K
-//                    survivors => the warp searches again from tau = +inf).  For every cell row within sqrt(tau) of the
-//                    query (conservative test on the row's y/z slab) the x interval that the ball can reach inside
-//                    that row is mapped to a position range; every candidate in it is evaluated with the PINNED fma
-//                    chain and kept when d <= tau (list in shared memory, arrival = ascending position).  When the
-//                    list overflows, and once at the end, the largest (distance, original index) keys are removed
-//                    until K remain.  Members are written in list order = ascending position in the cell arrangement,
-//                    a function of the cloud alone (never of the hint).
+//  geoa3_cell_sort   one CTA per cloud: bounding box, a grid of CUBIC cells (given, or sized per cloud from its surface
+//                    density so that a ball of `kref` points is about one cell wide), counting sort by cell with a rank
+//                    pass for the order inside a cell (cell-major, ascending original index: bitwise reproducible) ->
+//                    one blob per cloud: the cloud as float4 (x, y, z, original index) in cell order, the cell start
+//                    table and the inverse permutation (cells.cuh).  Cell index = (cz*gy + cy)*gx + cx, so one (cz, cy)
+//                    ROW of cells is one contiguous range of positions.
+//  geoa3_knn_cells   one query per thread, a warp's 32 queries are neighbours in cell order; the blob is staged by one
+//                    TMA bulk copy.  tau = largest pinned distance to the hinted candidates (previous step's
+//                    neighbours): an upper bound of the K-th distance whenever the hints are K-1 distinct points other
+//                    than the query (verified at the end: fewer than K survivors => the warp searches again from
+//                    tau = +inf).  For every cell row within sqrt(tau) of the query (conservative test on the row's
+//                    y/z slab) the x interval that the ball can reach inside that row is mapped to a position range;
+//                    every candidate in it is evaluated with the PINNED fma chain and kept when d <= tau (list in
+//                    shared memory, arrival = ascending position).  The largest (distance, original index) keys beyond
+//                    K are removed at the end (and whenever the list of the careful path overflows).  Members are
+//                    written in list order = ascending position in the cell arrangement, a function of the cloud and
+//                    its grid alone (never of the hint).
 //
-// Exactness.  cell(x) = trunc(clamp((x - lo) * inv_h, 0, G-1)) is monotone in x and is the SAME function on both
+// Exactness.  cell(x) = trunc(clamp((x - lo) * inv_h, 0, g-1)) is monotone in x and is the SAME float function on both
 // sides (sorting and querying), so |c.x - q.x| <= rx implies cell(q.x - rx) <= cell(c.x) <= cell(q.x + rx) whatever
 // the rounding; radii are inflated (relative 1e-5 + `slack` = 8e-6 * max|coordinate|, ~64 ulp of the largest
-// coordinate) over the rounding of the pinned chain (<= 5 ulp relative), of the cell boundaries and of the sums.
-// The grid only decides which candidates are LOOKED AT; what is kept is decided by the pinned arithmetic.
+// coordinate) over the rounding of the pinned chain (<= 5 ulp relative), of MUFU.RSQ, of the cell boundaries and of
+// the sums; the y/z slab test treats the LAST cell layer of an axis as unbounded (the clamp puts everything beyond the
+// grid there).  The grid only decides which candidates are LOOKED AT; what is kept is decided by the pinned arithmetic.
 #include <climits>
 
 #include "cells.cuh"
-#include "csr.cuh"
 
 #ifndef KC_EXTRA
 #define KC_EXTRA 11
