@@ -131,6 +131,21 @@ _LAST = {}  # (device, b, n, m) -> last results, reused as (non-aliased) hints b
 _ORDER = {}  # id(ori) -> (weakref(ori), version, perm, iperm, ori_arranged): visiting order of a cloud seen before
 
 
+USE_CELLS = True  # plain reference API: cell-grid searches for clouds of 32..CELLS_MAX_N points (A/B switch for tests)
+_CELLS = {}  # id(ori) -> (weakref(ori), version, Cells): cell grid of an original cloud seen before
+
+
+def _cells_of(ori_obj, ori_c):
+    ent = _CELLS.get(id(ori_obj))
+    if ent is not None and ent[0]() is ori_obj and ent[1] == ori_obj._version:
+        return ent[2]
+    cells = ops.cell_sort(ori_c, kref=HintBuffers.KREF_NN)
+    if len(_CELLS) > 8:
+        _CELLS.clear()
+    _CELLS[id(ori_obj)] = (weakref.ref(ori_obj), ori_obj._version, cells)
+    return cells
+
+
 def _order_of(ori_obj, ori_c):
     """Visiting order of an original cloud, cached per tensor object (the attack passes the same pc_ori every
     step).  Pure accelerator: the searches are exact for any order."""
@@ -167,6 +182,7 @@ def clear_cache():
     del _CACHE[:]
     _LAST.clear()
     _ORDER.clear()
+    _CELLS.clear()
 
 
 def _as_input(t, name):
@@ -210,13 +226,21 @@ def _nn(e, both):
         else:
             key = (e.adv_c.device, b, n, m)
             prev = _LAST.get(key)
-            kw = {}
-            if n == m and e.ori_ref() is not None:
-                perm, iperm, arranged = _order_of(e.ori_ref(), e.ori_c)
-                kw = dict(perm_a=perm, perm_o=perm, iperm_a=iperm, iperm_o=iperm, ori_arranged=arranged)
-            e.d1, e.jstar, e.d2, e.istar = ops.nn_pair(e.adv_c, e.ori_c, both=True,
-                                                       hint_a2o=prev[0] if prev else None,
-                                                       hint_o2a=prev[1] if prev else None, **kw)
+            if USE_CELLS and 32 <= n <= HintBuffers.CELLS_MAX_N and 32 <= m <= HintBuffers.CELLS_MAX_N and e.ori_ref() is not None:
+                # the reference API called step by step (chamfer_loss, hausdorff_loss, _get_kappa_adv ... on the same
+                # clouds): the cell-grid searches, seeded with the previous call's results
+                e.cells = ops.cell_sort(e.adv_c, kref=17.0)
+                e.d1, e.jstar, e.d2, e.istar = ops.nn_pair_cells(e.cells, _cells_of(e.ori_ref(), e.ori_c),
+                                                                 hint_a2o=prev[0] if prev else None,
+                                                                 hint_o2a=prev[1] if prev else None)
+            else:
+                kw = {}
+                if n == m and e.ori_ref() is not None:
+                    perm, iperm, arranged = _order_of(e.ori_ref(), e.ori_c)
+                    kw = dict(perm_a=perm, perm_o=perm, iperm_a=iperm, iperm_o=iperm, ori_arranged=arranged)
+                e.d1, e.jstar, e.d2, e.istar = ops.nn_pair(e.adv_c, e.ori_c, both=True,
+                                                           hint_a2o=prev[0] if prev else None,
+                                                           hint_o2a=prev[1] if prev else None, **kw)
             _LAST[key] = (e.jstar, e.istar)
         e.red = None
     return e
@@ -249,7 +273,11 @@ def _nbr(e, k):
             e.nbr[k] = hb.nbr[k]
         else:
             key = (e.adv_c.device,) + tuple(e.adv_c.shape) + (k,)
-            e.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=_LAST.get(key))[0]
+            prev = _LAST.get(key)
+            if e.cells is not None and prev is not None:   # member sets through this step's cell grid (kappa only sums)
+                e.nbr[k] = ops.knn_cells(e.cells, k + 1, drop=1, hint=prev)[0]
+            else:
+                e.nbr[k] = ops.knn(e.adv_c, e.adv_c, k + 1, drop=1, hint=prev)[0]
             _LAST[key] = e.nbr[k]
     return e.nbr[k]
 

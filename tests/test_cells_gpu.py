@@ -230,3 +230,36 @@ def test_fused_fwd_bwd_equals_two_kernels(b, n, k, std, single):
     with torch.no_grad():
         t2 = L.geo_loss(cu(adv), Oc, Nr, ko, k, 1.0, 0.1, 1.0, single_side=single, hints=L.HintBuffers())[0]
     assert float((t2 - res[False][0]).abs().max()) <= 2e-6 * float(t2.abs().max())
+
+
+def test_reference_api_cells_equal_scan():
+    """The reference's own call pattern (chamfer_loss, hausdorff_loss, _get_kappa_adv, curvature_loss called one after
+    the other on the same clouds, several steps in a row so that the second step is seeded by the first) with the
+    cell-grid searches and with the scanning kernels: same values and gradients up to summation-order rounding."""
+    from geoa3_b200 import loss_utils as L
+
+    b, n, k = 3, 1024, 16
+    adv0, ori, nrm = make(b, n, 5, 1e-2)
+    Oc, Nr = cu(ori), cu(nrm)
+    res = {}
+    for cells in (True, False):
+        L.USE_CELLS = cells
+        try:
+            L.clear_cache()
+            ko = L._get_kappa_ori(Oc, Nr, k)
+            cur, outs = adv0, []
+            for step in range(3):
+                cur = (cur + synth.make_offsets(b, n, seed=90 + step, std=4e-3)).astype(np.float32)
+                a = cu(cur).requires_grad_(True)
+                cd, hd = L.chamfer_loss(a, Oc), L.hausdorff_loss(a, Oc)
+                kap, _ = L._get_kappa_adv(a, Oc, Nr, k)
+                cv = L.curvature_loss(a, Oc, kap, ko)
+                (cd + 0.1 * hd + cv).sum().backward()
+                outs.append((cd.detach(), hd.detach(), cv.detach(), kap.detach(), a.grad.clone()))
+            res[cells] = outs
+        finally:
+            L.USE_CELLS = True
+    for s_c, s_s in zip(res[True], res[False]):
+        assert torch.equal(s_c[0], s_s[0]) and torch.equal(s_c[1], s_s[1])          # CD / HD: identical 1-NN results
+        for x, y in zip(s_c[2:], s_s[2:]):
+            assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max()) + 1e-12
