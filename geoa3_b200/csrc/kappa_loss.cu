@@ -522,7 +522,7 @@ geo_fwd_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori,
       s1 += d;
       if (d > mx) { mx = d; am = i; }  // ascending i per thread + strict '>' keeps the lowest index
     }
-    gkf[i] = gki;
+    if (do_curv) gkf[i] = gki;  // (no curvature term: the layout has no counter array, the factors stay 0)
   }
   float s2 = 0.f;
   if (d_o2a)
@@ -554,7 +554,8 @@ geo_fwd_bwd_kernel(const float* __restrict__ adv, const float* __restrict__ ori,
     }
   }
   // every kappa gather is done: the per-point curvature factors may now sit next to the coordinates
-  for (int i = tid; i < n; i += BW_THREADS) pts[i].w = gkf[i];
+  if (do_curv)
+    for (int i = tid; i < n; i += BW_THREADS) pts[i].w = gkf[i];
   __syncthreads();
 
   // ---- backward (the gather of loss_bwd_kernel, upstream gradient 1 per cloud)

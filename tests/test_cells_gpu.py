@@ -195,9 +195,11 @@ def test_hint_buffers_cells_equal_scan():
             assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max()) + 1e-12
 
 
-@pytest.mark.parametrize("b,n,k,std,single", [(4, 1024, 16, 1e-2, False), (3, 1000, 16, 3e-2, False), (2, 512, 32, 1e-2, True),
-                                              (2, 200, 2, 1e-1, False), (2, 2970, 16, 1e-2, False)])
-def test_fused_fwd_bwd_equals_two_kernels(b, n, k, std, single):
+@pytest.mark.parametrize("b,n,k,std,single,w_cu", [(4, 1024, 16, 1e-2, False, 1.0), (3, 1000, 16, 3e-2, False, 1.0),
+                                                   (2, 512, 32, 1e-2, True, 1.0), (2, 200, 2, 1e-1, False, 1.0),
+                                                   (2, 2970, 16, 1e-2, False, 1.0), (3, 1024, 16, 1e-2, False, 0.0),
+                                                   (2, 777, 16, 1e-2, True, 0.0)])
+def test_fused_fwd_bwd_equals_two_kernels(b, n, k, std, single, w_cu):
     """geoa3_geo_fwd_bwd (kappa + reductions + unit-upstream gradient in one launch, scaled in backward) against the
     two-kernel path (geoa3_kappa_loss_fwd, then geoa3_loss_bwd with the real upstream gradient): same losses, same
     gradient up to the rounding of (g*w)*x vs g*(w*x), for non-uniform upstream gradients, and bitwise reproducible."""
@@ -213,7 +215,7 @@ def test_fused_fwd_bwd_equals_two_kernels(b, n, k, std, single):
         try:
             L.clear_cache()
             a = cu(adv).requires_grad_(True)
-            tot, cd, hd, cv = L.geo_loss(a, Oc, Nr, ko, k, 1.0, 0.1, 1.0, single_side=single, hints=L.HintBuffers())
+            tot, cd, hd, cv = L.geo_loss(a, Oc, Nr, ko, k, 1.0, 0.1, w_cu, single_side=single, hints=L.HintBuffers())
             (tot * up).sum().backward()
             cur = (tot.detach().clone(), cd.clone(), hd.clone(), cv.clone(), a.grad.clone())
         finally:
@@ -228,7 +230,7 @@ def test_fused_fwd_bwd_equals_two_kernels(b, n, k, std, single):
     # forward only (no gradient requested): the two-kernel forward runs, same values
     L.clear_cache()
     with torch.no_grad():
-        t2 = L.geo_loss(cu(adv), Oc, Nr, ko, k, 1.0, 0.1, 1.0, single_side=single, hints=L.HintBuffers())[0]
+        t2 = L.geo_loss(cu(adv), Oc, Nr, ko, k, 1.0, 0.1, w_cu, single_side=single, hints=L.HintBuffers())[0]
     assert float((t2 - res[False][0]).abs().max()) <= 2e-6 * float(t2.abs().max())
 
 
