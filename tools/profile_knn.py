@@ -16,10 +16,10 @@ step = 0.01 if "--big-step" in sys.argv else 0.003
 adv_prev = adv - step * torch.sign(torch.randn_like(adv))
 nbr_prev = ops.knn(adv_prev, adv_prev, k + 1, drop=1)[0]          # knn_kernel launch 0: sorted, unhinted
 a = ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev)[0]            # knn_kernel launch 1: sorted, hinted
-for name, fn in (("kd", ops.kd_order), ("slab", ops.slab_order)):
+for name, fn in (("morton", ops.morton_order), ("slab", ops.slab_order)):
     p, ip = fn(ori)
     arr = ops.arrange(adv, p, with_bbox=True)
     m = ops.knn(adv, adv, k + 1, drop=1, hint=nbr_prev, perm_q=p, perm_c=p, iperm_c=ip, arranged=arr, members_only=True)[0]
-    assert torch.equal(m.sort(-1)[0], a.sort(-1)[0])              # knn_members launches 0 (kd), 1 (slab)
+    assert torch.equal(m.sort(-1)[0], a.sort(-1)[0])              # knn_members launches 0 (morton), 1 (slab)
 torch.cuda.synchronize()
 print("done")
