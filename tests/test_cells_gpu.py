@@ -265,3 +265,32 @@ def test_reference_api_cells_equal_scan():
         assert torch.equal(s_c[0], s_s[0]) and torch.equal(s_c[1], s_s[1])          # CD / HD: identical 1-NN results
         for x, y in zip(s_c[2:], s_s[2:]):
             assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max()) + 1e-12
+
+
+def test_full_batch_cells_parity_B250():
+    """BASELINE config[1] size, EVERY cloud against the C oracle: cell-grid 1-NN (both directions, distances and
+    argmins) and cell-grid kNN member sets (K = 17, hinted by the unperturbed cloud's lists), plus the size-independent
+    properties: results do not depend on the hint or on the grid, and a second call on its own output is a fixed point."""
+    from geoa3_b200 import ops
+
+    b, n, k = 250, 1024, 16
+    pc, _, _ = synth.make_batch(50, n, 0)
+    ori = np.tile(pc, (5, 1, 1))
+    adv = (ori + synth.make_offsets(b, n, seed=3, std=1e-2)).astype(np.float32)
+    A, Oc = cu(adv), cu(ori)
+    ca, co = ops.cell_sort(A, kref=k + 1), ops.cell_sort(Oc, kref=4)
+    d1, j1, d2, i2 = ops.nn_pair_cells(ca, co)
+    od1, oj1 = O.nn1(adv, ori)
+    od2, oi2 = O.nn1(ori, adv)
+    assert np.array_equal(j1.cpu().numpy(), oj1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    oi = O.knn(adv, adv, k + 1)[0][:, :, 1:]
+    hint = cu(O.knn(ori, ori, k + 1)[0][:, :, 1:])   # "previous step" = the unperturbed cloud
+    mem = ops.knn_cells(ca, k + 1, drop=1, hint=hint)[0]
+    assert np.array_equal(np.sort(mem.cpu().numpy(), -1), np.sort(oi, -1))
+    assert torch.equal(ops.knn_cells(ca, k + 1, drop=1, hint=mem)[0], mem)            # fixed point, same order
+    assert torch.equal(ops.knn_cells(ca, k + 1, drop=1)[0], mem)                      # no hint: same members, same order
+    other = ops.knn_cells(ops.cell_sort(A, grid=7), k + 1, drop=1, hint=hint)[0]      # another grid: same members
+    assert torch.equal(other.sort(-1)[0], mem.sort(-1)[0])
+    d1b, j1b, d2b, i2b = ops.nn_pair_cells(ops.cell_sort(A, grid=(5, 9, 3)), ops.cell_sort(Oc, grid=11), hint_a2o=i2[:, :n], hint_o2a=j1)
+    assert torch.equal(j1b, j1) and torch.equal(i2b, i2) and torch.equal(d1b, d1) and torch.equal(d2b, d2)
