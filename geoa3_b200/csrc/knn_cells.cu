@@ -501,61 +501,82 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int ncap, int k
     }
   }
 
-  // ---- careful path: no usable hint, or the fast path gave up.  Generic: the query itself is a candidate, the list
-  // is cut when it overflows (tau tightens), rows are the union of the warp's reach, the `drop` smallest keys are
-  // removed at the end; an invalid bound makes the warp search again from +inf.
-  bool act = careful;
-  if (!__any_sync(0xffffffffu, act)) return;
-  int cnt = 0;
-  bool rescan;
-  do {
-    int z0, z1, y0, y1;
-    {
-      const float r = sqrtf(tau * KC_REL) * KC_REL + slack;
-      z0 = act ? kc_cell(q.z - r, loz, ihz, gmz) : INT_MAX;
-      z1 = act ? kc_cell(q.z + r, loz, ihz, gmz) : -1;
-      y0 = act ? kc_cell(q.y - r, loy, ihy, gmy) : INT_MAX;
-      y1 = act ? kc_cell(q.y + r, loy, ihy, gmy) : -1;
-      z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
-      y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
-    }
-    for (int rz = z0; rz <= z1; ++rz) {
-      const float hz = sgp[8];
-      const float zl = fmaf((float)rz, hz, loz);
-      const float ez = fmaxf(fmaxf(zl - q.z, q.z - ((float)rz >= gmz ? KC_INF : zl + hz)) - slack, 0.f);
-      const float ez2 = ez * ez;
-      for (int ry = y0; ry <= y1; ++ry) {
-        const float hy = sgp[7];
-        const float yl = fmaf((float)ry, hy, loy);
-        const float ey = fmaxf(fmaxf(yl - q.y, q.y - ((float)ry >= gmy ? KC_INF : yl + hy)) - slack, 0.f);
-        const float rem = fmaf(tau, KC_REL, 1e-37f) - ez2 - ey * ey;
-        const bool ok = act && rem >= 0.f;
-        const float rx = sqrtf(fmaxf(rem, 0.f)) * KC_REL + slack;
-        const int base = (rz * gy + ry) * gx;
-        const int x0 = kc_cell(q.x - rx, lox, ihx, gmx), x1 = kc_cell(q.x + rx, lox, ihx, gmx);
-        const int s = scs[base + x0];
-        const int len = ok ? (int)scs[base + x1 + 1] - s : 0;
-        const int wl = __reduce_max_sync(0xffffffffu, len);
-        const float4* cp = s4 + s;
-#pragma unroll 1
-        for (int i = 0; i < wl; ++i) {
-          if (i < len) {
-            const float4 c = cp[i];
-            const float d = dist2(c.x, c.y, c.z, q.x, q.y, q.z);
-            if (d <= tau) {
-              if (cnt == R) cnt = kc_cut<T>(d_, v_, cnt, kk, &tau);  // makes room and tightens tau
-              d_[cnt * T] = d;
-              v_[cnt * T] = (uint16_t)__float_as_int(c.w);
-              ++cnt;
+  // ---- careful path: no usable hint, or the fast path gave up (list / row-table overflow, zero-distance duplicate,
+  // invalid bound, drop > 1).  Such queries are rare in an attack step but expensive (their bound is loose), so the warp
+  // takes them ONE AT A TIME with its 32 lanes on 32 consecutive candidates of a row: passes are appended in position
+  // order by ballot, the list is cut when it overflows (tau tightens), the query itself is a candidate like any other
+  // and the `drop` smallest keys are removed at the end; fewer than K survivors = the bound was not valid: the
+  // query is searched again from +inf.  (A lane-per-query walk made the whole warp wait on its one slow lane: up to
+  // 17 us of the kernel on late attack states.)
+  unsigned todo = __ballot_sync(0xffffffffu, careful);
+  const int lane = tid & 31;
+  while (todo) {
+    const int L = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const float qx = __shfl_sync(0xffffffffu, q.x, L), qy = __shfl_sync(0xffffffffu, q.y, L),
+                qz = __shfl_sync(0xffffffffu, q.z, L);
+    float tl = __shfl_sync(0xffffffffu, tau, L);  // the query's bound (warp-uniform from here on)
+    float* dc = d_ - lane + L;                    // the query's columns
+    uint16_t* vc = v_ - lane + L;
+    int cnt = 0;
+    for (;;) {
+      const float r = (tl < 3e38f ? kc_sqrt(tl * KC_REL) * KC_REL : KC_INF) + slack;
+      const int z0 = kc_cell(qz - r, loz, ihz, gmz), z1 = kc_cell(qz + r, loz, ihz, gmz);
+      const int y0 = kc_cell(qy - r, loy, ihy, gmy), y1 = kc_cell(qy + r, loy, ihy, gmy);
+      for (int rz = z0; rz <= z1; ++rz) {
+        const float hz = sgp[8];
+        const float zl = fmaf((float)rz, hz, loz);
+        const float ez = fmaxf(fmaxf(zl - qz, qz - ((float)rz >= gmz ? KC_INF : zl + hz)) - slack, 0.f);
+        for (int ry = y0; ry <= y1; ++ry) {
+          const float hy = sgp[7];
+          const float yl = fmaf((float)ry, hy, loy);
+          const float ey = fmaxf(fmaxf(yl - qy, qy - ((float)ry >= gmy ? KC_INF : yl + hy)) - slack, 0.f);
+          const float rem = fmaf(tl, KC_REL, 1e-37f) - ez * ez - ey * ey;  // with the CURRENT bound
+          if (!(rem >= 0.f)) continue;
+          const float rx = (rem < 3e38f ? kc_sqrt(rem) * KC_REL : KC_INF) + slack;
+          const int base = (rz * gy + ry) * gx;
+          const int s = scs[base + kc_cell(qx - rx, lox, ihx, gmx)], e = scs[base + kc_cell(qx + rx, lox, ihx, gmx) + 1];
+          for (int p0 = s; p0 < e; p0 += 32) {
+            const int pos = p0 + lane;
+            const float4 c = s4[min(pos, e - 1)];
+            const float d = dist2(c.x, c.y, c.z, qx, qy, qz);  // the pinned arithmetic decides
+            const int ci = __float_as_int(c.w);
+            const unsigned pass = __ballot_sync(0xffffffffu, pos < e && d <= tl);
+            if (cnt + __popc(pass) <= R) {
+              if ((pass >> lane) & 1u) {
+                const int slot = cnt + __popc(pass & ((1u << lane) - 1u));
+                dc[slot * T] = d;
+                vc[slot * T] = (uint16_t)ci;
+              }
+              cnt += __popc(pass);
+            } else {  // the list overflows inside this group: one entry at a time, cutting when full
+              unsigned m2 = pass;
+              while (m2) {
+                const int bl = __ffs(m2) - 1;
+                m2 &= m2 - 1;
+                const float db = __shfl_sync(0xffffffffu, d, bl);
+                const int cb = __shfl_sync(0xffffffffu, ci, bl);
+                if (db <= tl) {  // (tl may have dropped since the ballot)
+                  if (cnt == R) {
+                    __syncwarp();
+                    if (lane == 0) cnt = kc_cut<T>(dc, vc, cnt, kk, &tl);
+                    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                    tl = __shfl_sync(0xffffffffu, tl, 0);
+                  }
+                  if (lane == 0 && db <= tl) { dc[cnt * T] = db; vc[cnt * T] = (uint16_t)cb; }
+                  if (db <= tl) ++cnt;
+                }
+              }
             }
           }
         }
       }
+      if (cnt >= kk || !(tl < 3e38f)) break;  // (already searched from +inf: non-finite coordinates, nothing more to find)
+      tl = KC_INF;  // fewer than K survivors: the bound was not valid for this query
+      cnt = 0;
     }
-    // fewer than K survivors => the hinted bound was not valid for this query: the warp searches again from +inf
-    const bool fail = act && cnt < kk;
-    rescan = __any_sync(0xffffffffu, fail);
-    if (act && !fail) {
+    __syncwarp();
+    if (lane == L) {  // the query's own lane finishes its list (rare path: plain loops)
       kc_mark<T>(d_, v_, cnt, cnt - kk);
       for (int t = 0; t < drop; ++t) {  // the `drop` smallest (distance, original index) keys are no members
         float md = KC_INF;
@@ -571,10 +592,9 @@ knn_cells_kernel(const unsigned char* __restrict__ blobs, int n, int ncap, int k
         d_[bs * T] = -1.f;
       }
       kc_write<T>(d_, v_, cnt, kout, io, dn);
-      act = false;
     }
-    if (fail) { tau = KC_INF; cnt = 0; }
-  } while (rescan);
+    __syncwarp();
+  }
 }
 
 template <int K>
