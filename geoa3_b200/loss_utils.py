@@ -72,6 +72,13 @@ class HintBuffers(object):
         # launches read their hints from it instead of from the buffers they refresh, so a launch can be repeated
         # on the same (cloud, previous-step hint) pair.  Results never depend on hints, so this changes timing only.
         self.frozen = None
+        self._side = None
+
+    def side_stream(self, device):
+        """Stream the attack step runs the geometry losses on, next to the victim network (attack.forward_step)."""
+        if self._side is None or self._side.device != torch.device(device):
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
 
     def ensure_order(self, ori):
         if self.perm is None or self.perm.shape != (ori.shape[0], ori.shape[2]):
